@@ -1,0 +1,546 @@
+// C-ABI of libbloomrast (see include/bloomrast.h): stage orchestration, private state layout,
+// error handling.  Replaces the reference driver CudaRasterizer::Rasterizer::{forward, backward,
+// visible_filter, markVisible} (cuda_rasterizer/rasterizer_impl.cu:141-504) and its chunk
+// sub-allocator (rasterizer_impl.h:21-73, rasterizer_impl.cu:155-194).
+//
+// Stage order of brs_forward (all on the caller's stream):
+//   memset(header, ranges) -> preprocess -> [async copy of R to pinned host memory + event]
+//   -> depth sort (hist + 4 onesweep passes; does not need R, so the GPU stays busy while the host
+//      waits for the event) -> host: wait R, allocate binning/scratch -> scan+emit -> tile sort
+//   (hist + 1..3 passes) -> tile ranges -> blend.
+// brs_backward: memset(accumulator) -> blend backward -> fused preprocess backward.  No host sync.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace brs {
+
+namespace {
+
+thread_local long long t_launches = 0;
+thread_local int t_last_cuda_error = 0;
+
+struct HostSlot { // per thread: pinned word for the R readback + its event
+	int device = -1;
+	uint32_t* pinned = nullptr;
+	cudaEvent_t event = nullptr;
+};
+thread_local HostSlot t_slot;
+
+cudaError_t ensure_slot()
+{
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (t_slot.pinned != nullptr && t_slot.device == dev)
+		return cudaSuccess;
+	if (t_slot.pinned != nullptr) {
+		cudaFreeHost(t_slot.pinned);
+		cudaEventDestroy(t_slot.event);
+		t_slot = HostSlot{};
+	}
+	e = cudaHostAlloc(reinterpret_cast<void**>(&t_slot.pinned), 64, cudaHostAllocDefault);
+	if (e != cudaSuccess)
+		return e;
+	e = cudaEventCreateWithFlags(&t_slot.event, cudaEventDisableTiming);
+	if (e != cudaSuccess)
+		return e;
+	t_slot.device = dev;
+	return cudaSuccess;
+}
+
+inline int fail_cuda(cudaError_t e)
+{
+	t_last_cuda_error = (int)e;
+	return BRS_ERR_CUDA;
+}
+
+#define BRS_CUDA(expr)                                                                                                 \
+	do {                                                                                                               \
+		cudaError_t _e = (expr);                                                                                       \
+		if (_e != cudaSuccess)                                                                                         \
+			return fail_cuda(_e);                                                                                      \
+	} while (0)
+
+// reference CHECK_CUDA (auxiliary.h:166-173): only when debug, synchronise and surface errors
+#define BRS_STAGE(expr, debug, stream)                                                                                 \
+	do {                                                                                                               \
+		BRS_CUDA(expr);                                                                                                \
+		if (debug)                                                                                                     \
+			BRS_CUDA(cudaStreamSynchronize(stream));                                                                   \
+	} while (0)
+
+constexpr size_t HEADER_BYTES = 256;
+
+struct GeomLayout {
+	size_t header, records, depth_key, rect, order, total;
+};
+GeomLayout geom_layout(size_t P)
+{
+	GeomLayout l{};
+	size_t off = 0;
+	l.header = off;
+	off += HEADER_BYTES;
+	l.records = off;
+	off += align_up(sizeof(float4) * 3 * P, 256);
+	l.depth_key = off;
+	off += align_up(sizeof(uint32_t) * P, 256);
+	l.rect = off;
+	off += align_up(sizeof(uint2) * P, 256);
+	l.order = off;
+	off += align_up(sizeof(uint32_t) * P, 256);
+	l.total = off;
+	return l;
+}
+
+struct ImageLayout {
+	size_t ranges, final_T, n_contrib, total;
+};
+ImageLayout image_layout(int W, int H)
+{
+	ImageLayout l{};
+	const size_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+	const size_t npix = (size_t)W * H;
+	size_t off = 0;
+	l.ranges = off;
+	off += align_up(sizeof(uint2) * gx * gy, 256);
+	l.final_T = off;
+	off += align_up(sizeof(float) * npix, 256);
+	l.n_contrib = off;
+	off += align_up(sizeof(uint32_t) * npix, 256);
+	l.total = off < 256 ? 256 : off;
+	return l;
+}
+
+size_t binning_bytes(size_t R) { return align_up(sizeof(uint32_t) * (R ? R : 1), 256); }
+
+// reference getHigherMsb (rasterizer_impl.cu:35-50) yields the bit count the tile id is sorted on;
+// any bit count >= ceil(log2(#tiles)) gives the same order, so use the exact one.
+int tile_bits(uint32_t num_tiles)
+{
+	int b = 0;
+	while ((1ull << b) < (unsigned long long)num_tiles)
+		b++;
+	return b < 1 ? 1 : b;
+}
+
+int validate_view(const brs_view* v, bool need_campos_bg)
+{
+	if (v == nullptr || v->viewmatrix == nullptr || v->projmatrix == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	if (v->image_width < 0 || v->image_height < 0)
+		return BRS_ERR_INVALID_ARG;
+	if (v->image_width >= 65536 * TILE_X || v->image_height >= 65536 * TILE_Y)
+		return BRS_ERR_UNSUPPORTED; // tile coordinates are packed into 16 bits
+	if (need_campos_bg && v->bg == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	return BRS_OK;
+}
+
+int validate_gaussians(const brs_view* v, const brs_gaussians* g)
+{
+	if (g == nullptr || g->P < 0)
+		return BRS_ERR_INVALID_ARG;
+	if (g->P == 0)
+		return BRS_OK;
+	if (g->means3D == nullptr || g->opacities == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	// reference Python wrapper raises for both / neither (depth_diff_gaussian_rasterization/__init__.py:192-196)
+	if ((g->shs == nullptr) == (g->colors_precomp == nullptr))
+		return BRS_ERR_INVALID_ARG;
+	const bool has_sr = g->scales != nullptr && g->rotations != nullptr;
+	if (has_sr == (g->cov3D_precomp != nullptr))
+		return BRS_ERR_INVALID_ARG;
+	if (!has_sr && (g->scales != nullptr || g->rotations != nullptr))
+		return BRS_ERR_INVALID_ARG;
+	if (g->shs != nullptr) {
+		if (v->sh_degree < 0 || v->sh_degree > 3)
+			return BRS_ERR_UNSUPPORTED;
+		if (v->sh_coeffs < (v->sh_degree + 1) * (v->sh_degree + 1) || v->sh_coeffs > 16)
+			return BRS_ERR_INVALID_ARG;
+		if (v->campos == nullptr)
+			return BRS_ERR_INVALID_ARG;
+	}
+	return BRS_OK;
+}
+
+} // namespace
+
+void count_launch() { t_launches++; }
+
+} // namespace brs
+
+using namespace brs;
+
+extern "C" {
+
+int brs_version(void) { return BRS_VERSION; }
+
+long long brs_launch_count(int reset)
+{
+	long long v = t_launches;
+	if (reset)
+		t_launches = 0;
+	return v;
+}
+
+int brs_last_cuda_error(void) { return t_last_cuda_error; }
+const char* brs_last_cuda_error_string(void) { return cudaGetErrorString((cudaError_t)t_last_cuda_error); }
+
+const char* brs_error_string(int status)
+{
+	switch (status) {
+	case BRS_OK: return "ok";
+	case BRS_ERR_INVALID_ARG: return "invalid argument";
+	case BRS_ERR_ALLOC: return "allocator callback returned NULL";
+	case BRS_ERR_CUDA: return "CUDA error (see brs_last_cuda_error_string)";
+	case BRS_ERR_UNSUPPORTED: return "unsupported configuration";
+	case BRS_ERR_STATE: return "forward state does not match the given sizes";
+	default: return "unknown status";
+	}
+}
+
+size_t brs_geom_bytes(int P) { return geom_layout(P < 0 ? 0 : (size_t)P).total; }
+size_t brs_binning_bytes(int R) { return binning_bytes(R < 0 ? 0 : (size_t)R); }
+size_t brs_image_bytes(int W, int H) { return image_layout(W, H).total; }
+size_t brs_sort_scratch_bytes(int n) { return sort_scratch_bytes(n < 0 ? 0 : (size_t)n); }
+
+static size_t depth_scratch_bytes(size_t P) { return align_up(sizeof(uint32_t) * P, 256) + sort_scratch_bytes(P); }
+static size_t instance_scratch_bytes(size_t P, size_t R)
+{
+	return 3 * align_up(sizeof(uint32_t) * R, 256) + sort_scratch_bytes(R) + emit_scratch_bytes(P);
+}
+size_t brs_forward_scratch_bytes(int P, int R, int, int)
+{
+	return depth_scratch_bytes(P < 0 ? 0 : P) + instance_scratch_bytes(P < 0 ? 0 : P, R < 0 ? 0 : R);
+}
+size_t brs_backward_scratch_bytes(int P) { return align_up(sizeof(float) * ACCUM_STRIDE * (P < 0 ? 0 : (size_t)P), 256); }
+
+int brs_state_layout(int P, int R, int W, int H, brs_layout* out)
+{
+	if (out == nullptr || P < 0 || R < 0 || W < 0 || H < 0)
+		return BRS_ERR_INVALID_ARG;
+	const GeomLayout g = geom_layout(P);
+	const ImageLayout im = image_layout(W, H);
+	out->geom_records = g.records;
+	out->geom_depth_key = g.depth_key;
+	out->geom_rect = g.rect;
+	out->geom_order = g.order;
+	out->binning_point_list = 0;
+	out->image_ranges = im.ranges;
+	out->image_final_T = im.final_T;
+	out->image_n_contrib = im.n_contrib;
+	return BRS_OK;
+}
+
+int brs_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, int n,
+                       int begin_bit, int end_bit, void* scratch, brs_stream stream)
+{
+	if (n < 0 || begin_bit < 0 || end_bit > 32 || begin_bit > end_bit)
+		return BRS_ERR_INVALID_ARG;
+	if (n == 0)
+		return BRS_OK;
+	if (n > (1 << 30))
+		return BRS_ERR_UNSUPPORTED;
+	if (keys_in == nullptr || keys_out == nullptr || vals_out == nullptr || scratch == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	BRS_CUDA(sort_pairs(keys_in, vals_in, keys_out, vals_out, (size_t)n, begin_bit, end_bit, scratch, stream));
+	return BRS_OK;
+}
+
+int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, float* out_depth, int* radii,
+                brs_alloc_fn alloc, void* alloc_ctx, brs_fwd_state* state, brs_stream stream)
+{
+	int st = validate_view(view, true);
+	if (st != BRS_OK)
+		return st;
+	st = validate_gaussians(view, g);
+	if (st != BRS_OK)
+		return st;
+	if (alloc == nullptr || state == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	const int W = view->image_width, H = view->image_height, P = g->P;
+	const size_t npix = (size_t)W * H;
+	if ((npix > 0 && (out_color == nullptr || out_depth == nullptr)) || (P > 0 && radii == nullptr))
+		return BRS_ERR_INVALID_ARG;
+	const bool debug = view->debug != 0;
+
+	memset(state, 0, sizeof(*state));
+
+	if (P == 0) {
+		// reference rasterize_points.cu:68-82: outputs are zero-filled and no kernel runs (so the
+		// background is NOT composited when there are no Gaussians at all).
+		if (npix > 0) {
+			BRS_CUDA(cudaMemsetAsync(out_color, 0, sizeof(float) * NUM_CHANNELS * npix, stream));
+			BRS_CUDA(cudaMemsetAsync(out_depth, 0, sizeof(float) * npix, stream));
+		}
+		return BRS_OK;
+	}
+
+	const uint32_t grid_x = (W + TILE_X - 1) / TILE_X, grid_y = (H + TILE_Y - 1) / TILE_Y;
+	const GeomLayout gl = geom_layout(P);
+	const ImageLayout il = image_layout(W, H);
+
+	char* geom = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_GEOM, gl.total));
+	char* image = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_IMAGE, il.total));
+	if (geom == nullptr || image == nullptr)
+		return BRS_ERR_ALLOC;
+	state->geom = geom;
+	state->geom_bytes = gl.total;
+	state->image = image;
+	state->image_bytes = il.total;
+
+	uint32_t* d_total = reinterpret_cast<uint32_t*>(geom + gl.header);
+	float4* records = reinterpret_cast<float4*>(geom + gl.records);
+	uint32_t* depth_key = reinterpret_cast<uint32_t*>(geom + gl.depth_key);
+	uint2* rect = reinterpret_cast<uint2*>(geom + gl.rect);
+	uint32_t* order = reinterpret_cast<uint32_t*>(geom + gl.order);
+	uint2* ranges = reinterpret_cast<uint2*>(image + il.ranges);
+	float* final_T = reinterpret_cast<float*>(image + il.final_T);
+	uint32_t* n_contrib = reinterpret_cast<uint32_t*>(image + il.n_contrib);
+
+	BRS_CUDA(ensure_slot());
+	BRS_CUDA(cudaMemsetAsync(geom + gl.header, 0, HEADER_BYTES, stream));
+	if (grid_x * grid_y > 0)
+		BRS_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * grid_x * grid_y, stream)); // rasterizer_impl.cu:311
+
+	PreprocessArgs pa{};
+	pa.P = P;
+	pa.D = view->sh_degree;
+	pa.M = g->shs ? view->sh_coeffs : 0;
+	pa.means3D = g->means3D;
+	pa.scales = g->scales;
+	pa.scale_modifier = view->scale_modifier;
+	pa.rotations = g->rotations;
+	pa.opacities = g->opacities;
+	pa.shs = g->shs;
+	pa.cov3D_precomp = g->cov3D_precomp;
+	pa.colors_precomp = g->colors_precomp;
+	pa.viewmatrix = view->viewmatrix;
+	pa.projmatrix = view->projmatrix;
+	pa.campos = view->campos;
+	pa.W = W;
+	pa.H = H;
+	pa.tan_fovx = view->tanfovx;
+	pa.tan_fovy = view->tanfovy;
+	pa.focal_y = H / (2.0f * view->tanfovy); // rasterizer_impl.cu:223-224
+	pa.focal_x = W / (2.0f * view->tanfovx);
+	pa.grid_x = grid_x;
+	pa.grid_y = grid_y;
+	pa.prefiltered = view->prefiltered;
+	pa.radii = radii;
+	pa.records = records;
+	pa.depth_key = depth_key;
+	pa.rect = rect;
+	pa.total_tiles = d_total;
+	BRS_STAGE(launch_preprocess(pa, stream), debug, stream);
+
+	// R leaves for the host now; the depth sort below does not depend on it.
+	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	BRS_CUDA(cudaEventRecord(t_slot.event, stream));
+
+	char* scratch1 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, depth_scratch_bytes(P)));
+	if (scratch1 == nullptr)
+		return BRS_ERR_ALLOC;
+	uint32_t* sorted_depth = reinterpret_cast<uint32_t*>(scratch1);
+	BRS_STAGE(sort_pairs(depth_key, nullptr, sorted_depth, order, (size_t)P, 0, 32,
+	                     scratch1 + align_up(sizeof(uint32_t) * (size_t)P, 256), stream),
+	          debug, stream);
+
+	BRS_CUDA(cudaEventSynchronize(t_slot.event)); // the one host wait (reference: rasterizer_impl.cu:282)
+	const uint32_t R = *t_slot.pinned;
+	if (R > (1u << 30))
+		return BRS_ERR_UNSUPPORTED;
+	state->num_rendered = (int)R;
+
+	char* binning = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_BINNING, binning_bytes(R)));
+	if (binning == nullptr)
+		return BRS_ERR_ALLOC;
+	state->binning = binning;
+	state->binning_bytes = binning_bytes(R);
+	uint32_t* point_list = reinterpret_cast<uint32_t*>(binning);
+
+	if (R > 0) {
+		char* scratch2 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, instance_scratch_bytes(P, R)));
+		if (scratch2 == nullptr)
+			return BRS_ERR_ALLOC;
+		const size_t rb = align_up(sizeof(uint32_t) * (size_t)R, 256);
+		uint32_t* inst_keys = reinterpret_cast<uint32_t*>(scratch2);
+		uint32_t* inst_ids = reinterpret_cast<uint32_t*>(scratch2 + rb);
+		uint32_t* sorted_keys = reinterpret_cast<uint32_t*>(scratch2 + 2 * rb);
+		char* sort_scratch = scratch2 + 3 * rb;
+		char* emit_scratch = sort_scratch + sort_scratch_bytes(R);
+
+		BRS_STAGE(launch_emit(order, rect, (size_t)P, grid_x, inst_keys, inst_ids, (size_t)R, emit_scratch, stream), debug,
+		          stream);
+		BRS_STAGE(sort_pairs(inst_keys, inst_ids, sorted_keys, point_list, (size_t)R, 0, tile_bits(grid_x * grid_y),
+		                     sort_scratch, stream),
+		          debug, stream);
+		BRS_STAGE(launch_tile_ranges(sorted_keys, (size_t)R, ranges, stream), debug, stream);
+	}
+
+	BlendFwdArgs ba{};
+	ba.ranges = ranges;
+	ba.point_list = point_list;
+	ba.records = records;
+	ba.bg = view->bg;
+	ba.W = W;
+	ba.H = H;
+	ba.grid_x = grid_x;
+	ba.grid_y = grid_y;
+	ba.final_T = final_T;
+	ba.n_contrib = n_contrib;
+	ba.out_color = out_color;
+	ba.out_depth = out_depth;
+	BRS_STAGE(launch_blend_forward(ba, stream), debug, stream);
+	return BRS_OK;
+}
+
+int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii, const brs_fwd_state* state,
+                 const float* dL_dout_color, const float* dL_dout_depth, const brs_grads* grads, brs_alloc_fn alloc,
+                 void* alloc_ctx, brs_stream stream)
+{
+	(void)dL_dout_depth; // reference: plumbed, never used (backward.cu:443-554)
+	int st = validate_view(view, true);
+	if (st != BRS_OK)
+		return st;
+	st = validate_gaussians(view, g);
+	if (st != BRS_OK)
+		return st;
+	if (grads == nullptr || state == nullptr || alloc == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	const int P = g->P;
+	if (P == 0)
+		return BRS_OK;
+	const int W = view->image_width, H = view->image_height;
+	const int M = g->shs ? view->sh_coeffs : 0;
+	if (radii == nullptr || grads->dL_dmeans2D == nullptr || grads->dL_dcolors == nullptr ||
+	    grads->dL_dopacity == nullptr || grads->dL_dmeans3D == nullptr || grads->dL_dcov3D == nullptr ||
+	    grads->dL_dscales == nullptr || grads->dL_drotations == nullptr || (M > 0 && grads->dL_dsh == nullptr))
+		return BRS_ERR_INVALID_ARG;
+	const GeomLayout gl = geom_layout(P);
+	const ImageLayout il = image_layout(W, H);
+	const int R = state->num_rendered;
+	if (state->geom == nullptr || state->image == nullptr || state->geom_bytes < gl.total ||
+	    state->image_bytes < il.total || R < 0 || (R > 0 && (state->binning == nullptr || state->binning_bytes < binning_bytes(R))))
+		return BRS_ERR_STATE;
+	if ((size_t)W * H > 0 && dL_dout_color == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	const bool debug = view->debug != 0;
+	const uint32_t grid_x = (W + TILE_X - 1) / TILE_X, grid_y = (H + TILE_Y - 1) / TILE_Y;
+
+	const char* geom = static_cast<const char*>(state->geom);
+	const char* image = static_cast<const char*>(state->image);
+
+	float* accum = static_cast<float*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, brs_backward_scratch_bytes(P)));
+	if (accum == nullptr)
+		return BRS_ERR_ALLOC;
+	BRS_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * ACCUM_STRIDE * (size_t)P, stream));
+
+	if (R > 0 && grid_x * grid_y > 0) {
+		BlendBwdArgs bb{};
+		bb.ranges = reinterpret_cast<const uint2*>(image + il.ranges);
+		bb.point_list = reinterpret_cast<const uint32_t*>(state->binning);
+		bb.records = reinterpret_cast<const float4*>(geom + gl.records);
+		bb.bg = view->bg;
+		bb.W = W;
+		bb.H = H;
+		bb.grid_x = grid_x;
+		bb.grid_y = grid_y;
+		bb.final_T = reinterpret_cast<const float*>(image + il.final_T);
+		bb.n_contrib = reinterpret_cast<const uint32_t*>(image + il.n_contrib);
+		bb.dL_dpixels = dL_dout_color;
+		bb.accum = accum;
+		BRS_STAGE(launch_blend_backward(bb, stream), debug, stream);
+	}
+
+	PreprocessBwdArgs pb{};
+	pb.P = P;
+	pb.D = view->sh_degree;
+	pb.M = M;
+	pb.means3D = g->means3D;
+	pb.radii = radii;
+	pb.shs = g->shs;
+	pb.scales = g->scales;
+	pb.rotations = g->rotations;
+	pb.scale_modifier = view->scale_modifier;
+	pb.cov3D_precomp = g->cov3D_precomp;
+	pb.viewmatrix = view->viewmatrix;
+	pb.projmatrix = view->projmatrix;
+	pb.campos = view->campos;
+	pb.W = W;
+	pb.H = H;
+	pb.tan_fovx = view->tanfovx;
+	pb.tan_fovy = view->tanfovy;
+	pb.focal_y = H / (2.0f * view->tanfovy);
+	pb.focal_x = W / (2.0f * view->tanfovx);
+	pb.accum = accum;
+	pb.dL_dmeans2D = grads->dL_dmeans2D;
+	pb.dL_dcolors = grads->dL_dcolors;
+	pb.dL_dopacity = grads->dL_dopacity;
+	pb.dL_dmeans3D = grads->dL_dmeans3D;
+	pb.dL_dcov3D = grads->dL_dcov3D;
+	pb.dL_dsh = M > 0 ? grads->dL_dsh : nullptr;
+	pb.dL_dscales = grads->dL_dscales;
+	pb.dL_drotations = grads->dL_drotations;
+	BRS_STAGE(launch_preprocess_backward(pb, stream), debug, stream);
+	return BRS_OK;
+}
+
+int brs_visible_filter(const brs_view* view, int P, const float* means3D, const float* scales, int scales_stride,
+                       const float* rotations, const float* cov3D_precomp, int* radii, brs_stream stream)
+{
+	int st = validate_view(view, false);
+	if (st != BRS_OK)
+		return st;
+	if (P < 0)
+		return BRS_ERR_INVALID_ARG;
+	if (P == 0)
+		return BRS_OK;
+	const bool has_sr = scales != nullptr && rotations != nullptr;
+	if (means3D == nullptr || radii == nullptr || has_sr == (cov3D_precomp != nullptr) || (has_sr && scales_stride < 3))
+		return BRS_ERR_INVALID_ARG;
+	const int W = view->image_width, H = view->image_height;
+	FilterArgs fa{};
+	fa.P = P;
+	fa.means3D = means3D;
+	fa.scales = scales;
+	fa.scales_stride = scales_stride;
+	fa.scale_modifier = view->scale_modifier;
+	fa.rotations = rotations;
+	fa.cov3D_precomp = cov3D_precomp;
+	fa.viewmatrix = view->viewmatrix;
+	fa.projmatrix = view->projmatrix;
+	fa.W = W;
+	fa.H = H;
+	fa.tan_fovx = view->tanfovx;
+	fa.tan_fovy = view->tanfovy;
+	fa.focal_y = H / (2.0f * view->tanfovy);
+	fa.focal_x = W / (2.0f * view->tanfovx);
+	fa.grid_x = (W + TILE_X - 1) / TILE_X;
+	fa.grid_y = (H + TILE_Y - 1) / TILE_Y;
+	fa.prefiltered = view->prefiltered;
+	fa.radii = radii;
+	BRS_STAGE(launch_filter(fa, stream), view->debug != 0, stream);
+	return BRS_OK;
+}
+
+int brs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                     brs_stream stream)
+{
+	(void)projmatrix; // reference in_frustum computes p_proj but only tests view-space z (auxiliary.h:154)
+	if (P < 0)
+		return BRS_ERR_INVALID_ARG;
+	if (P == 0)
+		return BRS_OK;
+	if (means3D == nullptr || viewmatrix == nullptr || present == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	BRS_CUDA(launch_check_frustum(P, means3D, viewmatrix, present, stream));
+	return BRS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,498 @@
+// Binning for sm_100a: depth sort, instance emission, tile sort, tile ranges.
+//
+// The reference builds 64-bit keys (tile << 32 | depth bits) for all R (tile, Gaussian) instances
+// and runs one 6-pass CUB radix sort over 12-byte pairs (rasterizer_impl.cu:70-111, 278-318).
+// The same order — ascending (tile, depth bits, Gaussian id), which is what a stable sort of the
+// reference's emission order yields — is produced here with ~4x less memory traffic by splitting it:
+//
+//   1. stable sort of the P Gaussians by depth bits (u32 key, value = id; culled ones carry the
+//      key 0xFFFFFFFF and sink to the end)                                     -> `order`
+//   2. one fused kernel: exclusive scan of tiles-per-Gaussian in depth order (decoupled look-back)
+//      + emission of (tile id, Gaussian id) instances                           -> R pairs of 8 B
+//   3. stable sort of the instances by tile id only (ceil(log2(#tiles)) bits: 2 passes at 1080p)
+//   4. tile ranges from the sorted tile ids (reference identifyTileRanges, rasterizer_impl.cu:116-138)
+//
+// Because (1) is stable in id and (3) is stable, instances inside a tile end up ordered by
+// (depth bits, id): exactly the reference's sorted `point_list`.
+//
+// The sort itself is a hand-written onesweep: one upfront digit histogram per pass, then ONE kernel
+// per digit that ranks with warp match_any, resolves cross-tile offsets by chained decoupled
+// look-back (tiles take tickets from an atomic counter so predecessors are always resident), and
+// scatters through shared memory so global writes are coalesced per digit run.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace brs {
+
+namespace {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 pairs per tile
+constexpr int RADIX_MAX = 256;
+constexpr int MAX_PASSES = 4;
+
+constexpr uint32_t FLAG_LOCAL = 1u << 30; // tile-local count published
+constexpr uint32_t FLAG_INCL = 2u << 30;  // inclusive prefix published
+constexpr uint32_t FLAG_MASK = 3u << 30;
+constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Exclusive scan of one value per thread over a 256-thread block; also returns the block total.
+// s_warp must hold SORT_WARPS uint32.  Contains two __syncthreads.
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp, uint32_t& total)
+{
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= (uint32_t)o)
+			incl += n;
+	}
+	if (lane == 31)
+		s_warp[warp] = incl;
+	__syncthreads();
+	uint32_t warp_off = 0, tot = 0;
+#pragma unroll
+	for (int w = 0; w < SORT_WARPS; w++) {
+		const uint32_t c = s_warp[w];
+		if ((uint32_t)w < warp)
+			warp_off += c;
+		tot += c;
+	}
+	__syncthreads();
+	total = tot;
+	return warp_off + incl - v;
+}
+
+struct PassPlan {
+	int passes;
+	int shift[MAX_PASSES];
+	int bits[MAX_PASSES];
+};
+
+PassPlan plan_passes(int begin_bit, int end_bit)
+{
+	PassPlan p{};
+	int nbits = end_bit - begin_bit;
+	if (nbits < 1)
+		nbits = 1;
+	p.passes = (nbits + 7) / 8;
+	int base = nbits / p.passes, extra = nbits % p.passes, s = begin_bit;
+	for (int i = 0; i < p.passes; i++) {
+		p.bits[i] = base + (i < extra ? 1 : 0);
+		p.shift[i] = s;
+		s += p.bits[i];
+	}
+	return p;
+}
+
+struct HistArgs {
+	int passes;
+	int shift[MAX_PASSES];
+	int bits[MAX_PASSES];
+};
+
+// One read of the keys -> digit histograms of every pass.  Warp-aggregated (match_any) shared
+// atomics, so degenerate digit distributions (the top depth byte has ~5 values, neighbouring
+// instances share their tile's high digit) do not serialise.
+__global__ void __launch_bounds__(SORT_THREADS) histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                                HistArgs h, uint32_t* __restrict__ hist)
+{
+	__shared__ uint32_t s_hist[MAX_PASSES][RADIX_MAX];
+	for (int i = threadIdx.x; i < MAX_PASSES * RADIX_MAX; i += SORT_THREADS)
+		(&s_hist[0][0])[i] = 0;
+	__syncthreads();
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t stride = gridDim.x * SORT_THREADS;
+	// n rounded up so whole warps stay converged for match_any
+	const uint32_t n_round = (n + 31u) & ~31u;
+	for (uint32_t i = blockIdx.x * SORT_THREADS + threadIdx.x; i < n_round; i += stride) {
+		const bool valid = i < n;
+		const uint32_t key = valid ? __ldg(keys + i) : 0u;
+#pragma unroll
+		for (int p = 0; p < MAX_PASSES; p++) {
+			if (p < h.passes) {
+				const uint32_t d = (key >> h.shift[p]) & ((1u << h.bits[p]) - 1u);
+				const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
+				if (valid && (uint32_t)(__ffs(peers) - 1) == lane)
+					atomicAdd(&s_hist[p][d], (uint32_t)__popc(peers));
+			}
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < h.passes * RADIX_MAX; i += SORT_THREADS) {
+		const uint32_t c = (&s_hist[0][0])[i];
+		if (c)
+			atomicAdd(hist + i, c);
+	}
+}
+
+// One stable counting-sort pass over digit (key >> shift) & mask.
+__global__ void __launch_bounds__(SORT_THREADS)
+    onesweep_pass_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                         uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, uint32_t n, int shift, int bits,
+                         const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket)
+{
+	__shared__ uint32_t s_cnt[SORT_WARPS][RADIX_MAX];
+	__shared__ uint32_t s_keys[SORT_TILE];
+	__shared__ uint32_t s_vals[SORT_TILE];
+	__shared__ uint32_t s_digit_start[RADIX_MAX];
+	__shared__ uint32_t s_goff[RADIX_MAX];
+	__shared__ uint32_t s_warp[SORT_WARPS];
+	__shared__ uint32_t s_tile;
+
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t radix = 1u << bits, mask = radix - 1u;
+
+	if (tid == 0)
+		s_tile = atomicAdd(ticket, 1u);
+	for (int i = tid; i < SORT_WARPS * RADIX_MAX; i += SORT_THREADS)
+		(&s_cnt[0][0])[i] = 0;
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint32_t base = tile * SORT_TILE;
+	const uint32_t valid_count = min((uint32_t)SORT_TILE, n - base);
+
+	// ---- load (warp-striped: coalesced, and rank order == index order) ----
+	uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+	const uint32_t wbase = warp * (32 * SORT_ITEMS) + lane;
+#pragma unroll
+	for (int i = 0; i < SORT_ITEMS; i++) {
+		const uint32_t li = wbase + i * 32;
+		const bool valid = li < valid_count;
+		key[i] = valid ? __ldg(kin + base + li) : 0xffffffffu;
+		val[i] = valid ? (vin ? __ldg(vin + base + li) : base + li) : 0u;
+	}
+
+	// ---- rank inside the warp (stable): match_any groups equal digits, the group's first lane
+	//      bumps the warp-private counter ----
+#pragma unroll
+	for (int i = 0; i < SORT_ITEMS; i++) {
+		const bool valid = (wbase + i * 32) < valid_count;
+		const uint32_t d = (key[i] >> shift) & mask;
+		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
+		rank[i] = 0;
+		if (valid) {
+			const int leader = __ffs(peers) - 1;
+			uint32_t old = 0;
+			if ((int)lane == leader) {
+				old = s_cnt[warp][d];
+				s_cnt[warp][d] = old + __popc(peers);
+			}
+			old = __shfl_sync(peers, old, leader);
+			rank[i] = old + __popc(peers & lanemask_lt());
+		}
+		__syncwarp();
+	}
+	__syncthreads();
+
+	// ---- per digit: exclusive offsets of the warps, tile total ----
+	uint32_t total = 0;
+	if (tid < radix) {
+#pragma unroll
+		for (int w = 0; w < SORT_WARPS; w++) {
+			const uint32_t c = s_cnt[w][tid];
+			s_cnt[w][tid] = total;
+			total += c;
+		}
+		// publish before anything else so successors can make progress
+		st_relaxed(status + (size_t)tile * RADIX_MAX + tid, (tile == 0 ? FLAG_INCL : FLAG_LOCAL) | total);
+	}
+
+	// ---- where each digit starts inside this tile / inside the whole array ----
+	uint32_t dummy;
+	const uint32_t digit_start = block_exclusive_scan_256(total, s_warp, dummy);
+	const uint32_t bin_base = block_exclusive_scan_256(tid < radix ? __ldg(hist + tid) : 0u, s_warp, dummy);
+
+	// ---- decoupled look-back: sum of this digit's counts over all earlier tiles ----
+	if (tid < radix) {
+		uint32_t excl = 0;
+		if (tile > 0) {
+			int p = (int)tile - 1;
+			while (true) {
+				const uint32_t v = ld_relaxed(status + (size_t)p * RADIX_MAX + tid);
+				const uint32_t f = v & FLAG_MASK;
+				if (f == 0)
+					continue; // predecessor has not published yet
+				excl += v & VALUE_MASK;
+				if (f == FLAG_INCL)
+					break;
+				p--;
+			}
+			st_relaxed(status + (size_t)tile * RADIX_MAX + tid, FLAG_INCL | (excl + total));
+		}
+		s_digit_start[tid] = digit_start;
+		s_goff[tid] = bin_base + excl - digit_start; // global position = s_goff[d] + position in tile
+	}
+	__syncthreads();
+
+	// ---- scatter into shared memory in sorted-by-digit order ----
+#pragma unroll
+	for (int i = 0; i < SORT_ITEMS; i++) {
+		if ((wbase + i * 32) < valid_count) {
+			const uint32_t d = (key[i] >> shift) & mask;
+			const uint32_t pos = s_digit_start[d] + s_cnt[warp][d] + rank[i];
+			s_keys[pos] = key[i];
+			s_vals[pos] = val[i];
+		}
+	}
+	__syncthreads();
+
+	// ---- coalesced write-out: consecutive threads hold consecutive positions of a digit run ----
+#pragma unroll
+	for (int i = 0; i < SORT_ITEMS; i++) {
+		const uint32_t j = tid + i * SORT_THREADS;
+		if (j < valid_count) {
+			const uint32_t k = s_keys[j];
+			const uint32_t g = s_goff[(k >> shift) & mask] + j;
+			kout[g] = k;
+			vout[g] = s_vals[j];
+		}
+	}
+}
+
+struct SortScratch {
+	uint32_t* hist;   // [MAX_PASSES][RADIX_MAX]
+	uint32_t* ticket; // [MAX_PASSES] (+ padding)
+	uint32_t* status; // [MAX_PASSES][tiles][RADIX_MAX]
+	uint32_t* tmp_keys;
+	uint32_t* tmp_vals;
+	size_t zero_bytes; // prefix of the scratch that must be zero before sorting
+	size_t total_bytes;
+};
+
+SortScratch carve_sort_scratch(void* scratch, size_t n)
+{
+	SortScratch s{};
+	const size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+	char* p = static_cast<char*>(scratch);
+	size_t off = 0;
+	s.hist = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * MAX_PASSES * RADIX_MAX, 256);
+	s.ticket = reinterpret_cast<uint32_t*>(p + off);
+	off += 256;
+	s.status = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * MAX_PASSES * tiles * RADIX_MAX, 256);
+	s.zero_bytes = off;
+	s.tmp_keys = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * n, 256);
+	s.tmp_vals = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * n, 256);
+	s.total_bytes = off;
+	return s;
+}
+
+} // namespace
+
+size_t sort_scratch_bytes(size_t n) { return carve_sort_scratch(nullptr, n).total_bytes; }
+
+cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                       size_t n, int begin_bit, int end_bit, void* scratch, cudaStream_t stream)
+{
+	if (n == 0)
+		return cudaSuccess;
+	const PassPlan plan = plan_passes(begin_bit, end_bit);
+	SortScratch s = carve_sort_scratch(scratch, n);
+	const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+	cudaError_t e = cudaMemsetAsync(scratch, 0, s.zero_bytes, stream);
+	if (e != cudaSuccess)
+		return e;
+
+	HistArgs h{};
+	h.passes = plan.passes;
+	for (int i = 0; i < plan.passes; i++) {
+		h.shift[i] = plan.shift[i];
+		h.bits[i] = plan.bits[i];
+	}
+	size_t hist_blocks_sz = (n + SORT_THREADS * 8 - 1) / (SORT_THREADS * 8);
+	if (hist_blocks_sz > 148 * 4)
+		hist_blocks_sz = 148 * 4;
+	const uint32_t hist_blocks = (uint32_t)hist_blocks_sz;
+	histogram_kernel<<<hist_blocks, SORT_THREADS, 0, stream>>>(keys_in, (uint32_t)n, h, s.hist);
+	count_launch();
+
+	const uint32_t* kin = keys_in;
+	const uint32_t* vin = vals_in;
+	for (int p = 0; p < plan.passes; p++) {
+		const bool to_out = ((plan.passes - 1 - p) & 1) == 0;
+		uint32_t* ko = to_out ? keys_out : s.tmp_keys;
+		uint32_t* vo = to_out ? vals_out : s.tmp_vals;
+		onesweep_pass_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, ko, vo, (uint32_t)n, plan.shift[p],
+		                                                         plan.bits[p], s.hist + p * RADIX_MAX,
+		                                                         s.status + (size_t)p * tiles * RADIX_MAX,
+		                                                         s.ticket + p);
+		count_launch();
+		kin = ko;
+		vin = vo;
+	}
+	return cudaGetLastError();
+}
+
+// ---- fused scan + emission ----------------------------------------------------------------------
+
+namespace {
+
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_ITEMS = 4;
+constexpr int EMIT_TILE = EMIT_THREADS * EMIT_ITEMS; // Gaussians per block
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+    emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rect, uint32_t P, uint32_t grid_x,
+                uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ inst_ids, uint32_t R, uint32_t* status,
+                uint32_t* ticket)
+{
+	__shared__ uint32_t s_incl[EMIT_TILE]; // inclusive instance offsets inside this block
+	__shared__ uint32_t s_id[EMIT_TILE];
+	__shared__ uint2 s_rect[EMIT_TILE];
+	__shared__ uint32_t s_warp[SORT_WARPS];
+	__shared__ uint32_t s_bcast[2];
+
+	const uint32_t tid = threadIdx.x;
+	if (tid == 0)
+		s_bcast[0] = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const uint32_t blk = s_bcast[0];
+	const uint32_t first = blk * EMIT_TILE + tid * EMIT_ITEMS;
+
+	uint32_t cnt[EMIT_ITEMS];
+	uint32_t tsum = 0;
+#pragma unroll
+	for (int k = 0; k < EMIT_ITEMS; k++) {
+		const uint32_t s = first + k;
+		uint32_t id = 0;
+		uint2 r = make_uint2(0u, 0u);
+		if (s < P) {
+			id = __ldg(order + s);
+			r = __ldg(rect + id);
+		}
+		const uint32_t w = (r.x >> 16) - (r.x & 0xffffu);
+		const uint32_t h = (r.y >> 16) - (r.y & 0xffffu);
+		cnt[k] = w * h;
+		tsum += cnt[k];
+		s_id[tid * EMIT_ITEMS + k] = id;
+		s_rect[tid * EMIT_ITEMS + k] = r;
+	}
+	uint32_t block_total;
+	uint32_t run = block_exclusive_scan_256(tsum, s_warp, block_total);
+#pragma unroll
+	for (int k = 0; k < EMIT_ITEMS; k++) {
+		run += cnt[k];
+		s_incl[tid * EMIT_ITEMS + k] = run;
+	}
+
+	// chained scan over blocks (single value): decoupled look-back
+	if (tid == 0) {
+		uint32_t excl = 0;
+		if (blk == 0) {
+			st_relaxed(status, FLAG_INCL | block_total);
+		} else {
+			st_relaxed(status + blk, FLAG_LOCAL | block_total);
+			int p = (int)blk - 1;
+			while (true) {
+				const uint32_t v = ld_relaxed(status + p);
+				const uint32_t f = v & FLAG_MASK;
+				if (f == 0)
+					continue;
+				excl += v & VALUE_MASK;
+				if (f == FLAG_INCL)
+					break;
+				p--;
+			}
+			st_relaxed(status + blk, FLAG_INCL | (excl + block_total));
+		}
+		s_bcast[1] = excl;
+	}
+	__syncthreads();
+	const uint32_t gbase = s_bcast[1];
+
+	// balanced emission: one output slot per thread-iteration, owner found by binary search
+	for (uint32_t j = tid; j < block_total; j += EMIT_THREADS) {
+		int lo = 0, hi = EMIT_TILE - 1; // first index with s_incl > j
+		while (lo < hi) {
+			const int mid = (lo + hi) >> 1;
+			if (s_incl[mid] > j)
+				hi = mid;
+			else
+				lo = mid + 1;
+		}
+		const uint2 r = s_rect[lo];
+		const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
+		const uint32_t h = (r.y >> 16) - y0;
+		const uint32_t k = j - (s_incl[lo] - w * h);
+		const uint32_t ty = y0 + k / w, tx = x0 + (k - (k / w) * w);
+		const uint32_t g = gbase + j;
+		if (g < R) {
+			tile_keys[g] = ty * grid_x + tx;
+			inst_ids[g] = s_id[lo];
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256)
+    tile_ranges_kernel(const uint32_t* __restrict__ keys, uint32_t R, uint2* __restrict__ ranges)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R)
+		return;
+	const uint32_t cur = __ldg(keys + i);
+	if (i == 0)
+		ranges[cur].x = 0;
+	else {
+		const uint32_t prev = __ldg(keys + i - 1);
+		if (cur != prev) {
+			ranges[prev].y = i;
+			ranges[cur].x = i;
+		}
+	}
+	if (i == R - 1)
+		ranges[cur].y = R;
+}
+
+} // namespace
+
+size_t emit_scratch_bytes(size_t P)
+{
+	const size_t blocks = (P + EMIT_TILE - 1) / EMIT_TILE;
+	return align_up(256 + sizeof(uint32_t) * blocks, 256);
+}
+
+cudaError_t launch_emit(const uint32_t* order, const uint2* rect, size_t P, uint32_t grid_x, uint32_t* tile_keys,
+                        uint32_t* inst_ids, size_t R, void* scratch, cudaStream_t stream)
+{
+	if (P == 0)
+		return cudaSuccess;
+	const uint32_t blocks = (uint32_t)((P + EMIT_TILE - 1) / EMIT_TILE);
+	cudaError_t e = cudaMemsetAsync(scratch, 0, emit_scratch_bytes(P), stream);
+	if (e != cudaSuccess)
+		return e;
+	uint32_t* ticket = static_cast<uint32_t*>(scratch);
+	uint32_t* status = ticket + 64;
+	emit_kernel<<<blocks, EMIT_THREADS, 0, stream>>>(order, rect, (uint32_t)P, grid_x, tile_keys, inst_ids,
+	                                                 (uint32_t)R, status, ticket);
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_tile_ranges(const uint32_t* sorted_tile_keys, size_t R, uint2* ranges, cudaStream_t stream)
+{
+	if (R == 0)
+		return cudaSuccess;
+	tile_ranges_kernel<<<(uint32_t)((R + 255) / 256), 256, 0, stream>>>(sorted_tile_keys, (uint32_t)R, ranges);
+	count_launch();
+	return cudaGetLastError();
+}
+
+} // namespace brs

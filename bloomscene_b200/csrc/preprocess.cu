@@ -1,0 +1,376 @@
+// Per-Gaussian forward preprocessing for sm_100a.
+//
+//   preprocess_kernel      <- reference preprocessCUDA        (cuda_rasterizer/forward.cu:155-256)
+//   filter_kernel          <- reference filter_preprocessCUDA (forward.cu:260-335)
+//   check_frustum_kernel   <- reference checkFrustum          (rasterizer_impl.cu:54-66)
+//
+// What differs from the reference (layout / scheduling only — the arithmetic keeps its shapes):
+//   * one packed 48-byte blend record per Gaussian {x,y,hx,hy | conic a,b,c,opacity | r,g,b,depth}
+//     instead of five separate arrays, so the blend kernels gather three aligned float4s;
+//   * SH coefficients of the *visible* Gaussians of a block are staged through shared memory with
+//     coalesced 128-bit streaming loads (row pitch 13 float4 -> conflict-free per-thread reads);
+//   * cov3D and the `clamped` flags are not stored: the backward recomputes them bit-identically;
+//   * the per-Gaussian tile rectangle is stored packed (8 B) and the grid-wide instance count R is
+//     accumulated here with one integer atomic per block, so the host can read R while the depth
+//     sort is already running;
+//   * hx,hy: a conservative bounding box of the region where this Gaussian's alpha can reach 1/255
+//     (used by the blend kernels for warp-level culling; see cull_extent()).
+#include "common.cuh"
+#include "gaussian_math.cuh"
+#include "kernels.h"
+
+namespace brs {
+
+// ---- geometry shared by preprocess / filter ---------------------------------------------------
+
+// reference forward.cu:74-113
+__device__ __forceinline__ float3 compute_cov2d(const float3& mean, float focal_x, float focal_y, float tan_fovx,
+                                                float tan_fovy, const float* cov3D, const float* viewmatrix)
+{
+	float3 t = transform_point_4x3(mean, viewmatrix);
+
+	const float limx = 1.3f * tan_fovx;
+	const float limy = 1.3f * tan_fovy;
+	const float txtz = t.x / t.z;
+	const float tytz = t.y / t.z;
+	t.x = min(limx, max(-limx, txtz)) * t.z;
+	t.y = min(limy, max(-limy, tytz)) * t.z;
+
+	mat3 J = make_mat3(focal_x / t.z, 0.0f, -(focal_x * t.x) / (t.z * t.z), 0.0f, focal_y / t.z,
+	                   -(focal_y * t.y) / (t.z * t.z), 0, 0, 0);
+
+	mat3 W = make_mat3(viewmatrix[0], viewmatrix[4], viewmatrix[8], viewmatrix[1], viewmatrix[5], viewmatrix[9],
+	                   viewmatrix[2], viewmatrix[6], viewmatrix[10]);
+
+	mat3 T = mul(W, J);
+
+	mat3 Vrk = make_mat3(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+
+	mat3 cov = mul(mul(transpose(T), transpose(Vrk)), T);
+
+	cov.c[0].x += 0.3f;
+	cov.c[1].y += 0.3f;
+	return {float(cov.c[0].x), float(cov.c[0].y), float(cov.c[1].y)};
+}
+
+struct Geometry {
+	float depth;     // p_view.z
+	float2 xy;       // pixel-space centre
+	float3 cov;      // 2D covariance (a, b, c) after the +0.3 dilation
+	float3 conic;    // inverse
+	int radius;      // ceil(3 sqrt(lambda_max))
+	uint2 rect_min, rect_max;
+};
+
+// Everything of preprocessCUDA up to the tile rectangle (forward.cu:186-237). Returns false when
+// the reference would `return` early (culled / degenerate / zero-area rectangle).
+__device__ __forceinline__ bool compute_geometry(const float3 p_orig, const float* scales, int scales_stride,
+                                                 const float* rotations, const float* cov3D_precomp, int idx,
+                                                 float scale_modifier, const float* view, const float* proj, int W,
+                                                 int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y,
+                                                 uint32_t grid_x, uint32_t grid_y, bool prefiltered, Geometry& g)
+{
+	// in_frustum (auxiliary.h:139-164): only the view-space z test is live.
+	float3 p_view = transform_point_4x3(p_orig, view);
+	if (p_view.z <= 0.2f) {
+		if (prefiltered) {
+			printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+			__trap();
+		}
+		return false;
+	}
+
+	float4 p_hom = transform_point_4x4(p_orig, proj);
+	float p_w = 1.0f / (p_hom.w + 0.0000001f);
+	float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+
+	float cov3D[6];
+	if (cov3D_precomp != nullptr) {
+#pragma unroll
+		for (int i = 0; i < 6; i++)
+			cov3D[i] = __ldg(cov3D_precomp + 6 * (size_t)idx + i);
+	} else {
+		const float* sp = scales + (size_t)idx * scales_stride;
+		v3 s = make_v3(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2));
+		const float* rp = rotations + 4 * (size_t)idx;
+		float4 q = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
+		compute_cov3d(s, scale_modifier, q, cov3D);
+	}
+
+	float3 cov = compute_cov2d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, view);
+
+	float det = (cov.x * cov.z - cov.y * cov.y);
+	if (det == 0.0f)
+		return false;
+	float det_inv = 1.f / det;
+	g.conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+
+	float mid = 0.5f * (cov.x + cov.z);
+	float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+	float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+	float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+	float2 point_image = {ndc2pix(p_proj.x, W), ndc2pix(p_proj.y, H)};
+	uint2 rect_min, rect_max;
+	get_rect(point_image, my_radius, rect_min, rect_max, grid_x, grid_y);
+	if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0)
+		return false;
+
+	g.depth = p_view.z;
+	g.xy = point_image;
+	g.cov = cov;
+	g.radius = (int)my_radius; // reference: radii[idx] = my_radius (float -> int)
+	g.rect_min = rect_min;
+	g.rect_max = rect_max;
+	return true;
+}
+
+// Conservative half-extents (in pixels) of {pixel : the reference blend would NOT `continue`}.
+// The blend keeps a pair only if alpha = min(0.99, o*exp(power)) >= 1/255 with
+// power = -0.5 (a dx^2 + c dy^2) - b dx dy evaluated in fp32 (forward.cu:416-429), i.e. only if
+// f(d) = d^T Q d <= tau := 2 ln(255 o) up to fp32 evaluation noise.  The box of that ellipse is
+// |dx| <= sqrt(tau Q^-1_xx), |dy| <= sqrt(tau Q^-1_yy), computed here in fp64 from the SAME fp32
+// conic the blend uses, with tau inflated by a bound on the fp32 evaluation error over every pixel
+// this Gaussian can meet (|d| <= radius + tile).  Where no bound can be given the box is infinite
+// (no culling), where opacity < 1/255 it is empty (alpha <= o always).
+__device__ __forceinline__ float2 cull_extent(const float3 conic, float opacity, int radius)
+{
+	const float inf = __int_as_float(0x7f800000);
+	if (opacity < 1.0f / 255.0f)
+		return make_float2(-inf, -inf);
+	if (!(opacity <= 3.0e38f)) // NaN / inf opacity: let the blend decide
+		return make_float2(inf, inf);
+	const double a = conic.x, b = conic.y, c = conic.z;
+	const double det = a * c - b * b;
+	if (!(det > 0.0) || !(a > 0.0) || !(c > 0.0))
+		return make_float2(inf, inf);
+	const double dmax = (double)radius + (double)(TILE_X + 1);
+	const double eval_err = 8.0 * 5.9604644775390625e-08 * (fabs(a) + fabs(c) + 2.0 * fabs(b)) * dmax * dmax;
+	double tau = 2.0 * log(255.0 * (double)opacity);
+	tau = (tau + eval_err + 1e-4) * (1.0 + 1e-5);
+	const double hx = sqrt(tau * c / det);
+	const double hy = sqrt(tau * a / det);
+	if (!(hx < 1e30) || !(hy < 1e30))
+		return make_float2(inf, inf);
+	return make_float2((float)(hx * (1.0 + 1e-6) + 1e-3), (float)(hy * (1.0 + 1e-6) + 1e-3));
+}
+
+// ---- K1 -----------------------------------------------------------------------------------------
+
+constexpr int PRE_THREADS = 128;
+
+__device__ __forceinline__ void stage_camera(float* s_cam, const float* view, const float* proj, const float* campos)
+{
+	const int t = threadIdx.x;
+	if (t < 16)
+		s_cam[t] = __ldg(view + t);
+	else if (t < 32)
+		s_cam[t] = __ldg(proj + t - 16);
+	else if (t < 35 && campos != nullptr)
+		s_cam[t] = __ldg(campos + t - 32);
+}
+
+// VEC: rows are 16 coefficient triples (48 floats = 12 float4) and `shs` is 16-byte aligned.
+template <bool VEC>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs a)
+{
+	extern __shared__ float4 s_dyn[]; // SH staging (only when a.shs != nullptr)
+	__shared__ float s_cam[36];
+	__shared__ uint32_t s_vis[PRE_THREADS / 32];
+	__shared__ uint32_t s_tiles[PRE_THREADS / 32];
+
+	stage_camera(s_cam, a.viewmatrix, a.projmatrix, a.campos);
+	__syncthreads();
+	const float* view = s_cam;
+	const float* proj = s_cam + 16;
+
+	const int block_first = blockIdx.x * PRE_THREADS;
+	const int idx = block_first + threadIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+	Geometry g;
+	bool visible = false;
+	float3 p_orig = {0.f, 0.f, 0.f};
+	if (idx < a.P) {
+		const float* mp = a.means3D + 3 * (size_t)idx;
+		p_orig = {__ldg(mp), __ldg(mp + 1), __ldg(mp + 2)};
+		visible = compute_geometry(p_orig, a.scales, 3, a.rotations, a.cov3D_precomp, idx, a.scale_modifier, view, proj,
+		                           a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, a.grid_x, a.grid_y,
+		                           a.prefiltered != 0, g);
+	}
+
+	const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
+	uint32_t tiles = visible ? (g.rect_max.y - g.rect_min.y) * (g.rect_max.x - g.rect_min.x) : 0u;
+
+	// ---- colour ----
+	float3 rgb = {0.f, 0.f, 0.f};
+	if (a.shs != nullptr) {
+		if (lane == 0)
+			s_vis[warp] = vis_mask;
+		__syncthreads();
+		const int row_f = 3 * a.M; // floats per Gaussian
+		if (VEC) {
+			// 12 float4 per row, pitch 13 float4: lane-consecutive LDS.128 rows are conflict-free.
+			const float4* src = reinterpret_cast<const float4*>(a.shs) + (size_t)block_first * 12;
+#pragma unroll
+			for (int k = 0; k < 12; k++) {
+				const int f = threadIdx.x + PRE_THREADS * k;
+				const int row = f / 12, col = f - row * 12;
+				const bool want = (s_vis[row >> 5] >> (row & 31)) & 1u;
+				if (want)
+					s_dyn[row * 13 + col] = ldg_stream_f4(src + f);
+			}
+		} else {
+			float* s_sh = reinterpret_cast<float*>(s_dyn);
+			const int pitch = row_f | 1; // odd pitch: conflict-free scalar reads
+			const float* src = a.shs + (size_t)block_first * row_f;
+			const int total = PRE_THREADS * row_f;
+			for (int f = threadIdx.x; f < total; f += PRE_THREADS) {
+				const int row = f / row_f, col = f - row * row_f;
+				const bool want = (s_vis[row >> 5] >> (row & 31)) & 1u;
+				if (want)
+					s_sh[row * pitch + col] = __ldg(src + f);
+			}
+		}
+		__syncthreads();
+		if (visible) {
+			const v3 pos = make_v3(p_orig.x, p_orig.y, p_orig.z);
+			const v3 cam = make_v3(s_cam[32], s_cam[33], s_cam[34]);
+			v3 res;
+			if (VEC) {
+				// 12 conflict-free LDS.128 into registers (constant indices below keep c[] in registers).
+				float c[48];
+				const float4* row = s_dyn + threadIdx.x * 13;
+#pragma unroll
+				for (int k = 0; k < 12; k++) {
+					const float4 v = row[k];
+					c[4 * k] = v.x;
+					c[4 * k + 1] = v.y;
+					c[4 * k + 2] = v.z;
+					c[4 * k + 3] = v.w;
+				}
+				res = eval_sh(a.D, pos, cam, c);
+			} else {
+				res = eval_sh(a.D, pos, cam, reinterpret_cast<const float*>(s_dyn) + threadIdx.x * (row_f | 1));
+			}
+			// glm::max(result, 0.0f)  (forward.cu:67-70); the `clamped` flags are recomputed in backward.
+			rgb = {(res.x < 0.0f) ? 0.0f : res.x, (res.y < 0.0f) ? 0.0f : res.y, (res.z < 0.0f) ? 0.0f : res.z};
+		}
+	} else if (visible) {
+		const float* cp = a.colors_precomp + 3 * (size_t)idx;
+		rgb = {__ldg(cp), __ldg(cp + 1), __ldg(cp + 2)};
+	}
+
+	// ---- outputs ----
+	if (idx < a.P) {
+		if (visible) {
+			const float opacity = __ldg(a.opacities + idx);
+			const float2 h = cull_extent(g.conic, opacity, g.radius);
+			float4* rec = a.records + 3 * (size_t)idx;
+			rec[0] = make_float4(g.xy.x, g.xy.y, h.x, h.y);
+			rec[1] = make_float4(g.conic.x, g.conic.y, g.conic.z, opacity);
+			rec[2] = make_float4(rgb.x, rgb.y, rgb.z, g.depth);
+			a.radii[idx] = g.radius;
+			a.depth_key[idx] = __float_as_uint(g.depth);
+			a.rect[idx] = make_uint2(g.rect_min.x | (g.rect_max.x << 16), g.rect_min.y | (g.rect_max.y << 16));
+		} else {
+			a.radii[idx] = 0;
+			a.depth_key[idx] = DEPTH_KEY_CULLED;
+			a.rect[idx] = make_uint2(0u, 0u);
+		}
+	}
+
+	// ---- grid-wide instance count R (integer -> deterministic) ----
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		tiles += __shfl_xor_sync(0xffffffffu, tiles, o);
+	if (lane == 0)
+		s_tiles[warp] = tiles;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t sum = 0;
+#pragma unroll
+		for (int w = 0; w < PRE_THREADS / 32; w++)
+			sum += s_tiles[w];
+		if (sum)
+			atomicAdd(a.total_tiles, sum);
+	}
+}
+
+// ---- K10 ----------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) filter_kernel(FilterArgs a)
+{
+	__shared__ float s_cam[36];
+	stage_camera(s_cam, a.viewmatrix, a.projmatrix, nullptr);
+	__syncthreads();
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= a.P)
+		return;
+	const float* mp = a.means3D + 3 * (size_t)idx;
+	float3 p_orig = {__ldg(mp), __ldg(mp + 1), __ldg(mp + 2)};
+	Geometry g;
+	bool visible = compute_geometry(p_orig, a.scales, a.scales_stride, a.rotations, a.cov3D_precomp, idx,
+	                                a.scale_modifier, s_cam, s_cam + 16, a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x,
+	                                a.focal_y, a.grid_x, a.grid_y, a.prefiltered != 0, g);
+	a.radii[idx] = visible ? g.radius : 0;
+}
+
+// ---- K11 ----------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+    check_frustum_kernel(int P, const float* means3D, const float* viewmatrix, uint8_t* present)
+{
+	__shared__ float s_view[16];
+	if (threadIdx.x < 16)
+		s_view[threadIdx.x] = __ldg(viewmatrix + threadIdx.x);
+	__syncthreads();
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P)
+		return;
+	const float* mp = means3D + 3 * (size_t)idx;
+	float3 p_orig = {__ldg(mp), __ldg(mp + 1), __ldg(mp + 2)};
+	float3 p_view = transform_point_4x3(p_orig, s_view);
+	present[idx] = (p_view.z <= 0.2f) ? 0 : 1;
+}
+
+// ---- launchers ----------------------------------------------------------------------------------
+
+cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream)
+{
+	if (a.P <= 0)
+		return cudaSuccess;
+	const int blocks = (a.P + PRE_THREADS - 1) / PRE_THREADS;
+	size_t smem = 0;
+	bool vec = false;
+	if (a.shs != nullptr) {
+		vec = (a.M == 16) && ((reinterpret_cast<uintptr_t>(a.shs) & 15u) == 0);
+		smem = vec ? (size_t)PRE_THREADS * 13 * sizeof(float4) : (size_t)PRE_THREADS * ((3 * a.M) | 1) * sizeof(float);
+	}
+	if (vec)
+		preprocess_kernel<true><<<blocks, PRE_THREADS, smem, stream>>>(a);
+	else
+		preprocess_kernel<false><<<blocks, PRE_THREADS, smem, stream>>>(a);
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_filter(const FilterArgs& a, cudaStream_t stream)
+{
+	if (a.P <= 0)
+		return cudaSuccess;
+	filter_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_check_frustum(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                                 cudaStream_t stream)
+{
+	if (P <= 0)
+		return cudaSuccess;
+	check_frustum_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+	count_launch();
+	return cudaGetLastError();
+}
+
+} // namespace brs

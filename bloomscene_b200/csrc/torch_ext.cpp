@@ -1,0 +1,365 @@
+// Thin PyTorch binding over the C-ABI in include/bloomrast.h.  Compiled by g++ only (no CUDA code
+// here); every compute call goes through libbloomrast.so.
+//
+// Mirrors the reference's binding: module functions, argument order and return tuples of
+// ext.cpp:15-20 / rasterize_points.cu:35-288, so the reference's Python wrapper
+// (depth_diff_gaussian_rasterization/__init__.py) works unchanged on top of it:
+//   rasterize_gaussians(19 args)            -> (R, color, depth, radii, geomBuffer, binningBuffer, imgBuffer)
+//   rasterize_gaussians_backward(22 args)   -> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D,
+//                                               dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+//   rasterize_aussians_filter(13 args)      -> radii            (the reference's own spelling)
+//   mark_visible(means3D, view, proj)       -> bool[P]
+// Differences: work is issued on torch's CURRENT stream (the reference uses the legacy default
+// stream), gradient tensors are torch::empty (the kernels write every element), and C-ABI status
+// codes become exceptions here, never inside the library.
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/extension.h>
+
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/bloomrast.h"
+
+namespace {
+
+struct AllocCtx {
+	torch::TensorOptions byte_opts;
+	torch::Tensor geom, binning, image;
+	std::vector<torch::Tensor> scratch;
+};
+
+void* alloc_cb(void* vctx, int which, size_t bytes)
+{
+	auto* ctx = static_cast<AllocCtx*>(vctx);
+	try {
+		torch::Tensor t = torch::empty({(int64_t)bytes}, ctx->byte_opts);
+		void* p = t.data_ptr();
+		switch (which) {
+		case BRS_BUF_GEOM: ctx->geom = t; break;
+		case BRS_BUF_BINNING: ctx->binning = t; break;
+		case BRS_BUF_IMAGE: ctx->image = t; break;
+		default: ctx->scratch.push_back(t); break;
+		}
+		return p;
+	} catch (...) {
+		return nullptr; // no exceptions across the C ABI
+	}
+}
+
+void check_status(int st, const char* what)
+{
+	if (st == BRS_OK)
+		return;
+	std::string msg = std::string(what) + ": " + brs_error_string(st);
+	if (st == BRS_ERR_CUDA)
+		msg += std::string(" [") + brs_last_cuda_error_string() + "]";
+	TORCH_CHECK(false, msg);
+}
+
+// Absent optionals arrive as empty (CPU) tensors: reference Python passes torch.Tensor([])
+// (depth_diff_gaussian_rasterization/__init__.py:198-208) and relies on data_ptr()==nullptr.
+const float* opt_ptr(const torch::Tensor& t, torch::Tensor& keep, const char* name)
+{
+	if (!t.defined() || t.numel() == 0)
+		return nullptr;
+	TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+	TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
+	keep = t.contiguous();
+	return keep.data_ptr<float>();
+}
+
+const float* req_ptr(const torch::Tensor& t, torch::Tensor& keep, const char* name)
+{
+	TORCH_CHECK(t.defined() && t.is_cuda(), name, " must be a CUDA tensor");
+	TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
+	keep = t.contiguous();
+	return keep.data_ptr<float>();
+}
+
+brs_stream current_stream() { return reinterpret_cast<brs_stream>(c10::cuda::getCurrentCUDAStream().stream()); }
+
+} // namespace
+
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                       const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                       const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                       const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                       const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
+                       const torch::Tensor& campos, const bool prefiltered, const bool debug)
+{
+	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
+		AT_ERROR("means3D must have dimensions (num_points, 3)");
+	}
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
+	c10::cuda::CUDAGuard guard(means3D.device());
+
+	const int P = means3D.size(0);
+	const int H = image_height;
+	const int W = image_width;
+
+	auto float_opts = means3D.options().dtype(torch::kFloat32);
+	auto int_opts = means3D.options().dtype(torch::kInt32);
+	torch::Tensor out_color = torch::empty({3, H, W}, float_opts);
+	torch::Tensor out_depth = torch::empty({1, H, W}, float_opts);
+	torch::Tensor radii = torch::empty({P}, int_opts);
+
+	AllocCtx ctx;
+	ctx.byte_opts = torch::TensorOptions(torch::kByte).device(means3D.device());
+	ctx.geom = torch::empty({0}, ctx.byte_opts);
+	ctx.binning = torch::empty({0}, ctx.byte_opts);
+	ctx.image = torch::empty({0}, ctx.byte_opts);
+
+	torch::Tensor k[11];
+	brs_view view{};
+	view.image_width = W;
+	view.image_height = H;
+	view.tanfovx = tan_fovx;
+	view.tanfovy = tan_fovy;
+	view.scale_modifier = scale_modifier;
+	view.sh_degree = degree;
+	view.prefiltered = prefiltered;
+	view.debug = debug;
+	view.bg = req_ptr(background, k[0], "bg");
+	view.viewmatrix = req_ptr(viewmatrix, k[1], "viewmatrix");
+	view.projmatrix = req_ptr(projmatrix, k[2], "projmatrix");
+	view.campos = opt_ptr(campos, k[3], "campos");
+
+	brs_gaussians g{};
+	g.P = P;
+	g.means3D = req_ptr(means3D, k[4], "means3D");
+	g.opacities = P ? req_ptr(opacity, k[5], "opacities") : nullptr;
+	g.shs = opt_ptr(sh, k[6], "shs");
+	g.colors_precomp = opt_ptr(colors, k[7], "colors_precomp");
+	g.scales = opt_ptr(scales, k[8], "scales");
+	g.rotations = opt_ptr(rotations, k[9], "rotations");
+	g.cov3D_precomp = opt_ptr(cov3D_precomp, k[10], "cov3D_precomp");
+	view.sh_coeffs = (g.shs != nullptr) ? (int)sh.size(1) : 0; // rasterize_points.cu:84-88
+
+	brs_fwd_state state{};
+	int st = brs_forward(&view, &g, out_color.data_ptr<float>(), out_depth.data_ptr<float>(),
+	                     P ? radii.data_ptr<int>() : nullptr, alloc_cb, &ctx, &state, current_stream());
+	check_status(st, "rasterize_gaussians");
+	return std::make_tuple(state.num_rendered, out_color, out_depth, radii, ctx.geom, ctx.binning, ctx.image);
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor>
+RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D,
+                               const torch::Tensor& radii, const torch::Tensor& colors, const torch::Tensor& scales,
+                               const torch::Tensor& rotations, const float scale_modifier,
+                               const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                               const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                               const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+                               const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+                               const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
+                               const torch::Tensor& imageBuffer, const bool debug)
+{
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
+	c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	const int H = dL_dout_color.size(1);
+	const int W = dL_dout_color.size(2);
+
+	int M = 0;
+	if (sh.numel() != 0 && sh.size(0) != 0) {
+		M = sh.size(1);
+	}
+
+	auto opts = means3D.options().dtype(torch::kFloat32);
+	torch::Tensor dL_dmeans3D = torch::empty({P, 3}, opts);
+	torch::Tensor dL_dmeans2D = torch::empty({P, 3}, opts);
+	torch::Tensor dL_dcolors = torch::empty({P, 3}, opts);
+	torch::Tensor dL_dopacity = torch::empty({P, 1}, opts);
+	torch::Tensor dL_dcov3D = torch::empty({P, 6}, opts);
+	torch::Tensor dL_dsh = torch::empty({P, M, 3}, opts);
+	torch::Tensor dL_dscales = torch::empty({P, 3}, opts);
+	torch::Tensor dL_drotations = torch::empty({P, 4}, opts);
+
+	if (P != 0) {
+		AllocCtx ctx;
+		ctx.byte_opts = torch::TensorOptions(torch::kByte).device(means3D.device());
+
+		torch::Tensor k[13];
+		brs_view view{};
+		view.image_width = W;
+		view.image_height = H;
+		view.tanfovx = tan_fovx;
+		view.tanfovy = tan_fovy;
+		view.scale_modifier = scale_modifier;
+		view.sh_degree = degree;
+		view.sh_coeffs = M;
+		view.prefiltered = 0;
+		view.debug = debug;
+		view.bg = req_ptr(background, k[0], "bg");
+		view.viewmatrix = req_ptr(viewmatrix, k[1], "viewmatrix");
+		view.projmatrix = req_ptr(projmatrix, k[2], "projmatrix");
+		view.campos = opt_ptr(campos, k[3], "campos");
+
+		brs_gaussians g{};
+		g.P = P;
+		g.means3D = req_ptr(means3D, k[4], "means3D");
+		g.opacities = g.means3D; // not read by backward (opacity lives in the forward records); non-NULL for validation
+		g.shs = opt_ptr(sh, k[6], "shs");
+		g.colors_precomp = opt_ptr(colors, k[7], "colors_precomp");
+		g.scales = opt_ptr(scales, k[8], "scales");
+		g.rotations = opt_ptr(rotations, k[9], "rotations");
+		g.cov3D_precomp = opt_ptr(cov3D_precomp, k[10], "cov3D_precomp");
+
+		TORCH_CHECK(radii.is_cuda() && radii.scalar_type() == torch::kInt32, "radii must be a CUDA int32 tensor");
+		torch::Tensor radii_c = radii.contiguous();
+		const float* dcol = req_ptr(dL_dout_color, k[11], "dL_dout_color");
+		const float* ddepth = opt_ptr(dL_dout_depth, k[12], "dL_dout_depth");
+
+		torch::Tensor geom_c = geomBuffer.contiguous(), bin_c = binningBuffer.contiguous(),
+		              img_c = imageBuffer.contiguous();
+		brs_fwd_state state{};
+		state.geom = geom_c.data_ptr();
+		state.geom_bytes = (size_t)geom_c.numel();
+		state.binning = bin_c.numel() ? bin_c.data_ptr() : nullptr;
+		state.binning_bytes = (size_t)bin_c.numel();
+		state.image = img_c.data_ptr();
+		state.image_bytes = (size_t)img_c.numel();
+		state.num_rendered = R;
+
+		brs_grads grads{};
+		grads.dL_dmeans2D = dL_dmeans2D.data_ptr<float>();
+		grads.dL_dcolors = dL_dcolors.data_ptr<float>();
+		grads.dL_dopacity = dL_dopacity.data_ptr<float>();
+		grads.dL_dmeans3D = dL_dmeans3D.data_ptr<float>();
+		grads.dL_dcov3D = dL_dcov3D.data_ptr<float>();
+		grads.dL_dsh = M > 0 ? dL_dsh.data_ptr<float>() : nullptr;
+		grads.dL_dscales = dL_dscales.data_ptr<float>();
+		grads.dL_drotations = dL_drotations.data_ptr<float>();
+
+		int st = brs_backward(&view, &g, radii_c.data_ptr<int>(), &state, dcol, ddepth, &grads, alloc_cb, &ctx,
+		                      current_stream());
+		check_status(st, "rasterize_gaussians_backward");
+	}
+
+	return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+	                       dL_drotations);
+}
+
+torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix)
+{
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
+	c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	torch::Tensor present = torch::empty({P}, means3D.options().dtype(at::kBool));
+	if (P != 0) {
+		torch::Tensor k[3];
+		int st = brs_mark_visible(P, req_ptr(means3D, k[0], "means3D"), req_ptr(viewmatrix, k[1], "viewmatrix"),
+		                          req_ptr(projmatrix, k[2], "projmatrix"),
+		                          reinterpret_cast<uint8_t*>(present.data_ptr<bool>()), current_stream());
+		check_status(st, "mark_visible");
+	}
+	return present;
+}
+
+torch::Tensor RasterizeGaussiansfilterCUDA(const torch::Tensor& means3D, const torch::Tensor& scales,
+                                           const torch::Tensor& rotations, const float scale_modifier,
+                                           const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                           const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                                           const int image_height, const int image_width, const bool prefiltered,
+                                           const bool debug)
+{
+	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
+		AT_ERROR("means3D must have dimensions (num_points, 3)");
+	}
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
+	c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	torch::Tensor radii = torch::empty({P}, means3D.options().dtype(torch::kInt32));
+	if (P != 0) {
+		torch::Tensor k[6];
+		brs_view view{};
+		view.image_width = image_width;
+		view.image_height = image_height;
+		view.tanfovx = tan_fovx;
+		view.tanfovy = tan_fovy;
+		view.scale_modifier = scale_modifier;
+		view.prefiltered = prefiltered;
+		view.debug = debug;
+		view.viewmatrix = req_ptr(viewmatrix, k[0], "viewmatrix");
+		view.projmatrix = req_ptr(projmatrix, k[1], "projmatrix");
+
+		// BloomScene passes scales as a [:, :3] view of a [P,6] tensor (gaussian_renderer/__init__.py:344):
+		// read it in place through its row stride instead of materialising a copy.
+		const float* scales_ptr = nullptr;
+		int scales_stride = 3;
+		if (scales.defined() && scales.numel() != 0) {
+			TORCH_CHECK(scales.is_cuda() && scales.scalar_type() == torch::kFloat32, "scales must be CUDA float32");
+			if (scales.dim() == 2 && scales.stride(1) == 1 && scales.stride(0) >= 3) {
+				scales_ptr = scales.data_ptr<float>();
+				scales_stride = (int)scales.stride(0);
+			} else {
+				k[2] = scales.contiguous();
+				scales_ptr = k[2].data_ptr<float>();
+			}
+		}
+		int st = brs_visible_filter(&view, P, req_ptr(means3D, k[3], "means3D"), scales_ptr, scales_stride,
+		                            opt_ptr(rotations, k[4], "rotations"), opt_ptr(cov3D_precomp, k[5], "cov3D_precomp"),
+		                            radii.data_ptr<int>(), current_stream());
+		check_status(st, "rasterize_aussians_filter");
+	}
+	return radii;
+}
+
+// ---- extras used by tests / bench (not part of the reference surface) ----------------------------
+
+std::tuple<torch::Tensor, torch::Tensor> SortPairs(const torch::Tensor& keys, const c10::optional<torch::Tensor>& vals,
+                                                   int begin_bit, int end_bit)
+{
+	TORCH_CHECK(keys.is_cuda() && keys.scalar_type() == torch::kInt32 && keys.dim() == 1, "keys: 1-D CUDA int32");
+	c10::cuda::CUDAGuard guard(keys.device());
+	const int n = keys.numel();
+	torch::Tensor kin = keys.contiguous();
+	torch::Tensor vin;
+	const uint32_t* vptr = nullptr;
+	if (vals.has_value() && vals->defined()) {
+		TORCH_CHECK(vals->is_cuda() && vals->scalar_type() == torch::kInt32 && vals->numel() == n, "vals: CUDA int32 [n]");
+		vin = vals->contiguous();
+		vptr = reinterpret_cast<const uint32_t*>(vin.data_ptr<int>());
+	}
+	torch::Tensor kout = torch::empty_like(kin), vout = torch::empty_like(kin);
+	torch::Tensor scratch =
+	    torch::empty({(int64_t)brs_sort_scratch_bytes(n)}, torch::TensorOptions(torch::kByte).device(keys.device()));
+	int st = brs_sort_pairs_u32(reinterpret_cast<const uint32_t*>(kin.data_ptr<int>()), vptr,
+	                            reinterpret_cast<uint32_t*>(kout.data_ptr<int>()),
+	                            reinterpret_cast<uint32_t*>(vout.data_ptr<int>()), n, begin_bit, end_bit,
+	                            scratch.data_ptr(), current_stream());
+	check_status(st, "sort_pairs");
+	return std::make_tuple(kout, vout);
+}
+
+pybind11::dict StateLayout(int P, int R, int W, int H)
+{
+	brs_layout l{};
+	check_status(brs_state_layout(P, R, W, H, &l), "state_layout");
+	pybind11::dict d;
+	d["geom_records"] = l.geom_records;
+	d["geom_depth_key"] = l.geom_depth_key;
+	d["geom_rect"] = l.geom_rect;
+	d["geom_order"] = l.geom_order;
+	d["binning_point_list"] = l.binning_point_list;
+	d["image_ranges"] = l.image_ranges;
+	d["image_final_T"] = l.image_final_T;
+	d["image_n_contrib"] = l.image_n_contrib;
+	return d;
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
+{
+	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
+	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+	m.def("rasterize_aussians_filter", &RasterizeGaussiansfilterCUDA);
+	m.def("mark_visible", &markVisible);
+	m.def("sort_pairs", &SortPairs, pybind11::arg("keys"), pybind11::arg("vals") = pybind11::none(),
+	      pybind11::arg("begin_bit") = 0, pybind11::arg("end_bit") = 32);
+	m.def("state_layout", &StateLayout);
+	m.def("launch_count", [](bool reset) { return brs_launch_count(reset ? 1 : 0); }, pybind11::arg("reset") = false);
+	m.def("version", []() { return brs_version(); });
+}

@@ -1,0 +1,193 @@
+/*
+ * bloomrast.h — C-ABI of the B200-native differentiable Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for BloomScene's `submodules/depth-diff-gaussian-rasterization`.
+ * Every entry point replaces one member of the reference's C++ static API
+ * `CudaRasterizer::Rasterizer` (reference: cuda_rasterizer/rasterizer.h:24-105), which the
+ * reference's torch binding (rasterize_points.cu:35-288, ext.cpp:15-20) calls with raw device
+ * pointers.  Plain C: device pointers and sizes only, no torch / C++ types, no exceptions.
+ *
+ * Conventions (same as the reference unless stated):
+ *   - all arrays are fp32 / int32 device memory, densely packed, row-major as PyTorch lays them out;
+ *   - `viewmatrix` / `projmatrix` are 16 floats whose memory is the transpose of the maths matrix
+ *     (row-vector convention, reference scene/cameras.py:59-62);
+ *   - a NULL pointer means "optional input absent" — the reference relies on empty tensors having
+ *     data_ptr()==nullptr (forward.cu:205,241; backward.cu:390,394; rasterizer_impl.cu:322,453,481);
+ *   - every function is asynchronous on `stream` except where noted, re-entrant, and never owns
+ *     memory: buffers come from the caller through `brs_alloc_fn`;
+ *   - return value: BRS_OK (0) or a negative brs_status; brs_error_string() names it.
+ */
+#ifndef BLOOMRAST_H_
+#define BLOOMRAST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRS_VERSION 100 /* 0.1.0 */
+
+typedef struct CUstream_st* brs_stream; /* == cudaStream_t */
+
+typedef enum brs_status {
+	BRS_OK = 0,
+	BRS_ERR_INVALID_ARG = -1, /* NULL where required, negative size, both/neither of an either-or pair */
+	BRS_ERR_ALLOC = -2,       /* allocator callback returned NULL */
+	BRS_ERR_CUDA = -3,        /* a CUDA call failed; see brs_last_cuda_error() */
+	BRS_ERR_UNSUPPORTED = -4, /* e.g. sh_degree > 3, more than 2^30 tile instances */
+	BRS_ERR_STATE = -5        /* forward state handed to backward does not match the sizes given */
+} brs_status;
+
+/* Which caller-owned buffer an allocation request is for.  GEOM / BINNING / IMAGE are the three
+ * byte buffers the reference keeps on the autograd context (rasterize_points.cu:74-79, "geomBuffer",
+ * "binningBuffer", "imgBuffer"); SCRATCH is temporary and may be released when the call returns
+ * (stream-ordered). */
+typedef enum brs_buffer {
+	BRS_BUF_GEOM = 0,
+	BRS_BUF_BINNING = 1,
+	BRS_BUF_IMAGE = 2,
+	BRS_BUF_SCRATCH = 3
+} brs_buffer;
+
+/* Replaces the reference's three std::function<char*(size_t)> resize callbacks
+ * (rasterizer.h:34-36, rasterize_points.cu:27-33).  Must return device memory of at least `bytes`
+ * bytes aligned to 256 bytes, usable on the stream of the call, or NULL on failure. */
+typedef void* (*brs_alloc_fn)(void* ctx, int which /* brs_buffer */, size_t bytes);
+
+/* Per-call camera / configuration: the fields of GaussianRasterizationSettings
+ * (depth_diff_gaussian_rasterization/__init__.py:158-170). */
+typedef struct brs_view {
+	int image_width;
+	int image_height;
+	float tanfovx;
+	float tanfovy;
+	float scale_modifier;
+	int sh_degree;           /* active degree D, 0..3 */
+	int sh_coeffs;           /* M = coefficients stored per Gaussian (shs is [P, M, 3]); 0 without SH */
+	int prefiltered;         /* reference traps on the device if a culled point is seen with this set */
+	int debug;               /* synchronise + check after every stage (reference CHECK_CUDA) */
+	const float* bg;         /* [3]  device */
+	const float* viewmatrix; /* [16] device */
+	const float* projmatrix; /* [16] device */
+	const float* campos;     /* [3]  device */
+} brs_view;
+
+/* Gaussian attributes, device pointers (reference rasterizer.h:37-52). Exactly one of
+ * shs / colors_precomp and exactly one of (scales, rotations) / cov3D_precomp is non-NULL. */
+typedef struct brs_gaussians {
+	int P;
+	const float* means3D;        /* [P,3] */
+	const float* opacities;      /* [P]   */
+	const float* shs;            /* [P,M,3] or NULL */
+	const float* colors_precomp; /* [P,3]   or NULL */
+	const float* scales;         /* [P,3]   or NULL */
+	const float* rotations;      /* [P,4]   or NULL (not normalised in-kernel, forward.cu:127) */
+	const float* cov3D_precomp;  /* [P,6]   or NULL */
+} brs_gaussians;
+
+/* What forward leaves behind for backward (the reference's geom/binning/img chunks + num_rendered). */
+typedef struct brs_fwd_state {
+	void* geom;
+	size_t geom_bytes;
+	void* binning;
+	size_t binning_bytes;
+	void* image;
+	size_t image_bytes;
+	int num_rendered; /* R = number of (tile, Gaussian) instances */
+} brs_fwd_state;
+
+/* Gradient outputs (reference rasterize_points.cu:154-162).  Every pointer that is non-NULL is
+ * fully written by brs_backward (zeros for Gaussians that were not rendered) — the caller does
+ * NOT need to zero-fill.  dL_dconic is internal in the reference and is not exposed. */
+typedef struct brs_grads {
+	float* dL_dmeans2D;   /* [P,3], z = 0   */
+	float* dL_dcolors;    /* [P,3]          */
+	float* dL_dopacity;   /* [P,1]          */
+	float* dL_dmeans3D;   /* [P,3]          */
+	float* dL_dcov3D;     /* [P,6]          */
+	float* dL_dsh;        /* [P,M,3] or NULL when M == 0 */
+	float* dL_dscales;    /* [P,3]          */
+	float* dL_drotations; /* [P,4]          */
+} brs_grads;
+
+/* --- entry points ------------------------------------------------------------------------- */
+
+/* Replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:32-57, rasterizer_impl.cu:198-339).
+ * Writes out_color [3,H,W] (planar), out_depth [1,H,W], radii [P]; all three are fully written.
+ * P == 0 writes zeros and returns R = 0 (reference skips the kernels: rasterize_points.cu:82).
+ * Performs ONE host wait (for R, to size the binning buffer) like the reference
+ * (rasterizer_impl.cu:282) — but overlapped with the depth sort. */
+int brs_forward(const brs_view* view, const brs_gaussians* g,
+                float* out_color, float* out_depth, int* radii,
+                brs_alloc_fn alloc, void* alloc_ctx,
+                brs_fwd_state* state, brs_stream stream);
+
+/* Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:78-105, rasterizer_impl.cu:403-504).
+ * dL_dout_depth is accepted and ignored: the reference plumbs it but every use is commented out
+ * (backward.cu:443-554), so depth carries no gradient.  No host synchronisation. */
+int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
+                 const brs_fwd_state* state,
+                 const float* dL_dout_color, const float* dL_dout_depth,
+                 const brs_grads* grads,
+                 brs_alloc_fn alloc, void* alloc_ctx, brs_stream stream);
+
+/* Replaces CudaRasterizer::Rasterizer::visible_filter (rasterizer.h:59-76, rasterizer_impl.cu:342-398):
+ * radii only.  `scales_stride` is the row stride of `scales` in floats (3 when dense); BloomScene
+ * passes a [:, :3] view of a [P,6] tensor (gaussian_renderer/__init__.py:344).  No allocations. */
+int brs_visible_filter(const brs_view* view, int P, const float* means3D,
+                       const float* scales, int scales_stride, const float* rotations,
+                       const float* cov3D_precomp, int* radii, brs_stream stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-30, rasterizer_impl.cu:141-153):
+ * present[i] = (view-space z of mean i) > 0.2. */
+int brs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, brs_stream stream);
+
+/* Buffer sizes: pure functions of the sizes (the reference re-derives its layout in backward the
+ * same way: rasterizer_impl.h:66-72 `required<T>`). */
+size_t brs_geom_bytes(int P);
+size_t brs_binning_bytes(int num_rendered);
+size_t brs_image_bytes(int image_width, int image_height);
+size_t brs_forward_scratch_bytes(int P, int num_rendered, int image_width, int image_height);
+size_t brs_backward_scratch_bytes(int P);
+
+/* Stable LSD radix sort of (u32 key, u32 value) pairs on key bits [begin_bit, end_bit) — the
+ * hand-written onesweep-style sort that replaces cub::DeviceRadixSort::SortPairs
+ * (rasterizer_impl.cu:304-309).  If vals_in is NULL the values are 0..n-1.  `scratch` must hold
+ * brs_sort_scratch_bytes(n) bytes; sorted output lands in keys_out / vals_out. */
+size_t brs_sort_scratch_bytes(int n);
+int brs_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in,
+                       uint32_t* keys_out, uint32_t* vals_out, int n,
+                       int begin_bit, int end_bit, void* scratch, brs_stream stream);
+
+/* Layout of the private state, for stage-level parity tests (offsets in bytes from the start of
+ * each buffer; strides in bytes). */
+typedef struct brs_layout {
+	/* geom */
+	size_t geom_records;   /* float4[3*P]: {x,y,hx,hy} {conic a,b,c,opacity} {r,g,b,depth} */
+	size_t geom_depth_key; /* u32[P]: float bits of view-space depth, 0xFFFFFFFF when culled */
+	size_t geom_rect;      /* u32[2*P]: (x0 | x1<<16), (y0 | y1<<16) tile rectangle */
+	size_t geom_order;     /* u32[P]: Gaussian ids sorted by (depth, id) */
+	/* binning */
+	size_t binning_point_list; /* u32[R]: Gaussian ids sorted by (tile, depth, id) */
+	/* image */
+	size_t image_ranges;    /* uint2[ceil(W/16)*ceil(H/16)] */
+	size_t image_final_T;   /* f32[W*H] */
+	size_t image_n_contrib; /* u32[W*H] */
+} brs_layout;
+int brs_state_layout(int P, int num_rendered, int image_width, int image_height, brs_layout* out);
+
+const char* brs_error_string(int status);
+/* cudaError_t of the last failing CUDA call on this thread (0 if none), and its name. */
+int brs_last_cuda_error(void);
+const char* brs_last_cuda_error_string(void);
+int brs_version(void);
+/* Number of kernels this library launched on the calling thread since the last reset. */
+long long brs_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOOMRAST_H_ */

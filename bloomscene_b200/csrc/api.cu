@@ -13,6 +13,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -53,6 +55,47 @@ cudaError_t ensure_slot()
 	return cudaSuccess;
 }
 
+// Optional per-stage CUDA-event timing (brs_stage_timing / brs_stage_times).
+struct StageTimer {
+	bool enabled = false;
+	struct Pending { int stage; cudaEvent_t a, b; };
+	std::vector<Pending> pending;
+	std::vector<cudaEvent_t> pool;
+	cudaEvent_t get()
+	{
+		if (!pool.empty()) {
+			cudaEvent_t e = pool.back();
+			pool.pop_back();
+			return e;
+		}
+		cudaEvent_t e = nullptr;
+		cudaEventCreate(&e);
+		return e;
+	}
+};
+thread_local StageTimer t_timer;
+
+struct StageScope {
+	int stage;
+	cudaStream_t stream;
+	cudaEvent_t a = nullptr;
+	StageScope(int stage_, cudaStream_t s) : stage(stage_), stream(s)
+	{
+		if (t_timer.enabled) {
+			a = t_timer.get();
+			cudaEventRecord(a, stream);
+		}
+	}
+	~StageScope()
+	{
+		if (a != nullptr) {
+			cudaEvent_t b = t_timer.get();
+			cudaEventRecord(b, stream);
+			t_timer.pending.push_back({stage, a, b});
+		}
+	}
+};
+
 inline int fail_cuda(cudaError_t e)
 {
 	t_last_cuda_error = (int)e;
@@ -67,8 +110,9 @@ inline int fail_cuda(cudaError_t e)
 	} while (0)
 
 // reference CHECK_CUDA (auxiliary.h:166-173): only when debug, synchronise and surface errors
-#define BRS_STAGE(expr, debug, stream)                                                                                 \
+#define BRS_STAGE(stage_id, expr, debug, stream)                                                                       \
 	do {                                                                                                               \
+		StageScope _scope(stage_id, stream);                                                                           \
 		BRS_CUDA(expr);                                                                                                \
 		if (debug)                                                                                                     \
 			BRS_CUDA(cudaStreamSynchronize(stream));                                                                   \
@@ -237,6 +281,55 @@ int brs_state_layout(int P, int R, int W, int H, brs_layout* out)
 	return BRS_OK;
 }
 
+void brs_stage_timing(int enable) { t_timer.enabled = enable != 0; }
+
+int brs_stage_times(float* ms, int* calls)
+{
+	for (auto& p : t_timer.pending) {
+		BRS_CUDA(cudaEventSynchronize(p.b));
+		float t = 0.f;
+		BRS_CUDA(cudaEventElapsedTime(&t, p.a, p.b));
+		if (p.stage >= 0 && p.stage < BRS_NUM_STAGES) {
+			if (ms)
+				ms[p.stage] += t;
+			if (calls)
+				calls[p.stage] += 1;
+		}
+		t_timer.pool.push_back(p.a);
+		t_timer.pool.push_back(p.b);
+	}
+	t_timer.pending.clear();
+	return BRS_OK;
+}
+
+double brs_probe_fp32_tflops(brs_stream stream) { return probe_fp32_tflops(stream); }
+
+int brs_count_pairs(const brs_view* view, const brs_fwd_state* state, int P, unsigned long long* out, brs_stream stream)
+{
+	if (view == nullptr || state == nullptr || out == nullptr || P < 0)
+		return BRS_ERR_INVALID_ARG;
+	const int W = view->image_width, H = view->image_height;
+	const GeomLayout gl = geom_layout(P);
+	const ImageLayout il = image_layout(W, H);
+	if (P == 0 || state->geom == nullptr || state->image == nullptr) {
+		BRS_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(unsigned long long), stream));
+		return BRS_OK;
+	}
+	const char* geom = static_cast<const char*>(state->geom);
+	char* image = static_cast<char*>(state->image);
+	BlendFwdArgs ba{};
+	ba.ranges = reinterpret_cast<const uint2*>(image + il.ranges);
+	ba.point_list = reinterpret_cast<const uint32_t*>(state->binning);
+	ba.records = reinterpret_cast<const float4*>(geom + gl.records);
+	ba.W = W;
+	ba.H = H;
+	ba.grid_x = (W + TILE_X - 1) / TILE_X;
+	ba.grid_y = (H + TILE_Y - 1) / TILE_Y;
+	ba.n_contrib = reinterpret_cast<uint32_t*>(image + il.n_contrib);
+	BRS_CUDA(launch_count_pairs(ba, out, stream));
+	return BRS_OK;
+}
+
 int brs_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, int n,
                        int begin_bit, int end_bit, void* scratch, brs_stream stream)
 {
@@ -337,7 +430,7 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	pa.depth_key = depth_key;
 	pa.rect = rect;
 	pa.total_tiles = d_total;
-	BRS_STAGE(launch_preprocess(pa, stream), debug, stream);
+	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
 
 	// R leaves for the host now; the depth sort below does not depend on it.
 	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -347,7 +440,7 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	if (scratch1 == nullptr)
 		return BRS_ERR_ALLOC;
 	uint32_t* sorted_depth = reinterpret_cast<uint32_t*>(scratch1);
-	BRS_STAGE(sort_pairs(depth_key, nullptr, sorted_depth, order, (size_t)P, 0, 32,
+	BRS_STAGE(BRS_STAGE_DEPTH_SORT, sort_pairs(depth_key, nullptr, sorted_depth, order, (size_t)P, 0, 32,
 	                     scratch1 + align_up(sizeof(uint32_t) * (size_t)P, 256), stream),
 	          debug, stream);
 
@@ -375,12 +468,12 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 		char* sort_scratch = scratch2 + 3 * rb;
 		char* emit_scratch = sort_scratch + sort_scratch_bytes(R);
 
-		BRS_STAGE(launch_emit(order, rect, (size_t)P, grid_x, inst_keys, inst_ids, (size_t)R, emit_scratch, stream), debug,
+		BRS_STAGE(BRS_STAGE_EMIT, launch_emit(order, rect, (size_t)P, grid_x, inst_keys, inst_ids, (size_t)R, emit_scratch, stream), debug,
 		          stream);
-		BRS_STAGE(sort_pairs(inst_keys, inst_ids, sorted_keys, point_list, (size_t)R, 0, tile_bits(grid_x * grid_y),
+		BRS_STAGE(BRS_STAGE_TILE_SORT, sort_pairs(inst_keys, inst_ids, sorted_keys, point_list, (size_t)R, 0, tile_bits(grid_x * grid_y),
 		                     sort_scratch, stream),
 		          debug, stream);
-		BRS_STAGE(launch_tile_ranges(sorted_keys, (size_t)R, ranges, stream), debug, stream);
+		BRS_STAGE(BRS_STAGE_TILE_RANGES, launch_tile_ranges(sorted_keys, (size_t)R, ranges, stream), debug, stream);
 	}
 
 	BlendFwdArgs ba{};
@@ -396,7 +489,7 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	ba.n_contrib = n_contrib;
 	ba.out_color = out_color;
 	ba.out_depth = out_depth;
-	BRS_STAGE(launch_blend_forward(ba, stream), debug, stream);
+	BRS_STAGE(BRS_STAGE_BLEND_FWD, launch_blend_forward(ba, stream), debug, stream);
 	return BRS_OK;
 }
 
@@ -455,7 +548,7 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 		bb.n_contrib = reinterpret_cast<const uint32_t*>(image + il.n_contrib);
 		bb.dL_dpixels = dL_dout_color;
 		bb.accum = accum;
-		BRS_STAGE(launch_blend_backward(bb, stream), debug, stream);
+		BRS_STAGE(BRS_STAGE_BLEND_BWD, launch_blend_backward(bb, stream), debug, stream);
 	}
 
 	PreprocessBwdArgs pb{};
@@ -487,7 +580,7 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 	pb.dL_dsh = M > 0 ? grads->dL_dsh : nullptr;
 	pb.dL_dscales = grads->dL_dscales;
 	pb.dL_drotations = grads->dL_drotations;
-	BRS_STAGE(launch_preprocess_backward(pb, stream), debug, stream);
+	BRS_STAGE(BRS_STAGE_PREPROCESS_BWD, launch_preprocess_backward(pb, stream), debug, stream);
 	return BRS_OK;
 }
 
@@ -525,7 +618,7 @@ int brs_visible_filter(const brs_view* view, int P, const float* means3D, const 
 	fa.grid_y = (H + TILE_Y - 1) / TILE_Y;
 	fa.prefiltered = view->prefiltered;
 	fa.radii = radii;
-	BRS_STAGE(launch_filter(fa, stream), view->debug != 0, stream);
+	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_filter(fa, stream), view->debug != 0, stream);
 	return BRS_OK;
 }
 

@@ -131,6 +131,10 @@ struct PreprocessBwdArgs {
 };
 cudaError_t launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t stream);
 
+// ---- measure.cu (bench / profiling only) ----------------------------------------------------------
+cudaError_t launch_count_pairs(const BlendFwdArgs& a, unsigned long long* out, cudaStream_t stream);
+double probe_fp32_tflops(cudaStream_t stream);
+
 constexpr int ACCUM_STRIDE = 12; // floats per Gaussian in the blend-backward accumulator
 
 } // namespace brs

@@ -351,8 +351,49 @@ pybind11::dict StateLayout(int P, int R, int W, int H)
 	return d;
 }
 
+// (E, C, E_b) pair counts of a finished forward, reference semantics (measurement only).
+std::tuple<int64_t, int64_t, int64_t> CountPairs(const torch::Tensor& geom, const torch::Tensor& binning,
+                                                 const torch::Tensor& image, int P, int R, int W, int H)
+{
+	c10::cuda::CUDAGuard guard(geom.device());
+	brs_view view{};
+	view.image_width = W;
+	view.image_height = H;
+	brs_fwd_state state{};
+	state.geom = geom.data_ptr();
+	state.geom_bytes = (size_t)geom.numel();
+	state.binning = binning.numel() ? binning.data_ptr() : nullptr;
+	state.binning_bytes = (size_t)binning.numel();
+	state.image = image.data_ptr();
+	state.image_bytes = (size_t)image.numel();
+	state.num_rendered = R;
+	torch::Tensor out = torch::zeros({3}, torch::TensorOptions(torch::kInt64).device(geom.device()));
+	check_status(brs_count_pairs(&view, &state, P, reinterpret_cast<unsigned long long*>(out.data_ptr<int64_t>()),
+	                             current_stream()),
+	             "count_pairs");
+	torch::Tensor h = out.cpu();
+	return std::make_tuple(h[0].item<int64_t>(), h[1].item<int64_t>(), h[2].item<int64_t>());
+}
+
+pybind11::dict StageTimes()
+{
+	float ms[BRS_NUM_STAGES] = {0};
+	int calls[BRS_NUM_STAGES] = {0};
+	check_status(brs_stage_times(ms, calls), "stage_times");
+	static const char* names[BRS_NUM_STAGES] = {"preprocess", "depth_sort", "emit", "tile_sort", "tile_ranges",
+	                                            "blend_fwd", "blend_bwd", "preprocess_bwd"};
+	pybind11::dict d;
+	for (int i = 0; i < BRS_NUM_STAGES; i++)
+		d[names[i]] = pybind11::make_tuple(ms[i], calls[i]);
+	return d;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 {
+	m.def("count_pairs", &CountPairs);
+	m.def("stage_timing", [](bool enable) { brs_stage_timing(enable ? 1 : 0); });
+	m.def("stage_times", &StageTimes);
+	m.def("probe_fp32_tflops", []() { return brs_probe_fp32_tflops(current_stream()); });
 	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
 	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
 	m.def("rasterize_aussians_filter", &RasterizeGaussiansfilterCUDA);

@@ -187,6 +187,38 @@ int brs_version(void);
 /* Number of kernels this library launched on the calling thread since the last reset. */
 long long brs_launch_count(int reset);
 
+/* --- measurement hooks (bench / profiling only; off by default) ---------------------------- */
+
+/* Stage ids for brs_stage_times(). */
+enum {
+	BRS_STAGE_PREPROCESS = 0,
+	BRS_STAGE_DEPTH_SORT = 1,
+	BRS_STAGE_EMIT = 2,
+	BRS_STAGE_TILE_SORT = 3,
+	BRS_STAGE_TILE_RANGES = 4,
+	BRS_STAGE_BLEND_FWD = 5,
+	BRS_STAGE_BLEND_BWD = 6,
+	BRS_STAGE_PREPROCESS_BWD = 7,
+	BRS_NUM_STAGES = 8
+};
+/* When enabled, every stage is bracketed by CUDA events on the call's stream (per thread). */
+void brs_stage_timing(int enable);
+/* Synchronises the recorded events; adds the accumulated milliseconds per stage into ms[BRS_NUM_STAGES]
+ * and the number of timed launches per stage into calls[BRS_NUM_STAGES] (either may be NULL),
+ * then clears the accumulators. */
+int brs_stage_times(float* ms, int* calls);
+
+/* Counts (pixel, instance) pairs of a finished forward under the REFERENCE's per-pixel semantics
+ * (forward.cu:409-452): out[0] = E pairs evaluated until each pixel's own stop, out[1] = C pairs
+ * that contribute, out[2] = E_b = sum of n_contrib (pairs the backward replays).  `out` is 3 x u64
+ * device memory.  Used for the roofline's algorithmic flop count. */
+int brs_count_pairs(const brs_view* view, const brs_fwd_state* state, int P, unsigned long long* out,
+                    brs_stream stream);
+
+/* FP32 FMA micro-benchmark: returns the achieved TFLOP/s of a dependent-FFMA kernel filling the
+ * GPU (the denominator for the blend kernels' roofline); synchronous. */
+double brs_probe_fp32_tflops(brs_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

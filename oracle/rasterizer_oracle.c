@@ -8,7 +8,7 @@
  * Parity status: the reference ships no tests, golden vectors or CPU implementation for this path
  * ("parity unpinned" by the reference itself).  This restatement is pinned instead against
  * outputs of the reference's OWN CUDA code (oracle/_ref, built from /root/reference) captured on a
- * B200: tests/golden/*.npz + tests/golden/make_golden.py.  Integer outputs agree except for rare
+ * B200: tests/golden/ (npz files) + tests/golden/make_golden.py.  Integer outputs agree except for rare
  * +-1 cases at ceil()/tile-edge boundaries, because the GPU build fuses multiply-adds (nvcc
  * -fmad=true) and uses its own expf, which plain C cannot reproduce bit for bit; floats agree to
  * ~1e-6.  The CUDA-vs-CUDA comparison on the GPU box is what defines bit-exactness.

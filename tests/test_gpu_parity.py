@@ -1,0 +1,287 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).
+
+Three independent checkers for the CUDA library, all driven through the public binding / C-ABI:
+  1. the reference's OWN CUDA rasterizer (oracle/_ref/_ref_C.so, built from /root/reference) on the
+     same tensors — bit-exact integers, colour/depth <= 1e-5, gradients rel-L2 <= 1e-4;
+  2. golden vectors captured from that reference (tests/golden/*.npz) — same bars, no reference needed;
+  3. the CPU oracle (oracle/rasterizer_oracle.c) on small scenes, and size-independent properties at
+     BASELINE.json's full sizes (sorted keys, range partition, bg linearity, determinism).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity_lib as pl
+from bloomscene_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _ref_or_skip():
+    ref = pl.reference()
+    if ref is None:
+        pytest.skip("oracle/_ref/_ref_C.so not built (needs /root/reference at build time)")
+    return ref
+
+
+def _assert_stage_parity(rep):
+    for k in ("radii_mismatch", "depth_bits_mismatch", "means2D_mismatch", "conic_opacity_mismatch",
+              "tiles_touched_mismatch", "point_list_mismatch", "ranges_mismatch", "sorted_keys_mismatch",
+              "n_contrib_mismatch", "final_T_mismatch"):
+        if k in rep:
+            assert rep[k] == 0, (k, rep)
+    assert rep["R_ours"] == rep["R_ref"], rep
+    if "unsorted_keys_multiset_equal" in rep:
+        assert rep["unsorted_keys_multiset_equal"]
+    assert rep.get("color_maxabs", 0.0) <= pl.COLOR_TOL, rep
+    assert rep.get("depth_maxabs", 0.0) <= pl.COLOR_TOL, rep
+
+
+def _assert_grad_parity(rep):
+    assert rep["radii_mismatch"] == 0
+    assert rep["color_maxabs"] <= pl.COLOR_TOL and rep["depth_maxabs"] <= pl.COLOR_TOL, rep
+    for k, v in rep.items():
+        if k.startswith("grad_"):
+            assert v <= pl.GRAD_TOL, (k, rep)  # relative L2 <= 1e-4
+
+
+CASES = [
+    # name, P, kind, color, mu, (W, H), yaw, bg, scale_modifier
+    ("p1_tile", 1, "object", "sh0", -2.0, (16, 16), 0.0, (0, 0, 0), 1.0),
+    ("p17_ragged", 17, "object", "sh3", -3.0, (17, 33), 0.3, (0.2, 0.5, 0.7), 1.0),
+    ("p1000_sh1", 1000, "object", "sh1", -3.5, (130, 70), 1.0, (0, 0, 0), 1.0),
+    ("p1000_sh2m16", 1000, "object", "sh2m16", -3.5, (64, 64), 2.0, (1, 1, 1), 1.0),
+    ("p5000_sh0m16", 5000, "object", "sh0m16", -3.8, (200, 120), 0.0, (0, 0, 0), 0.7),
+    ("p20k_precomp", 20_000, "object", "precomp", -4.0, (256, 256), 0.5, (0.1, 0.1, 0.1), 1.3),
+    ("band_mostly_culled", 30_000, "band", "precomp", -4.0, (128, 128), 0.7, (0, 0, 0), 1.0),
+    ("A_100k_sh0", 100_000, "object", "sh0", -4.0, (512, 512), 0.0, (0, 0, 0), 1.0),
+]
+
+
+def _make(case):
+    name, P, kind, color, mu, (W, H), yaw, bg, mod = case
+    scene = synthetic.make_scene(P, kind, color, mu, seed=sum(map(ord, name)) % 1000).to(DEV)
+    cam = (synthetic.orbit_camera(W, H, yaw) if kind == "object" else synthetic.yaw_camera(W, H, yaw)).to(DEV)
+    return scene, cam, torch.tensor(bg, dtype=torch.float32, device=DEV), mod
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_stages_bit_exact_vs_reference_cuda(case):
+    _ref_or_skip()
+    scene, cam, bg, mod = _make(case)
+    _assert_stage_parity(pl.compare_stages(scene, cam, bg, scale_modifier=mod))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_autograd_vs_reference_cuda(case):
+    _ref_or_skip()
+    scene, cam, bg, mod = _make(case)
+    Wc, Wd = (t.to(DEV) for t in synthetic.loss_weights(cam.image_width, cam.image_height))
+    _assert_grad_parity(pl.compare_autograd(scene, cam, bg, Wc, Wd, scale_modifier=mod))
+
+
+def test_cov3d_precomp_vs_reference_cuda():
+    _ref_or_skip()
+    from golden.make_golden import cov3d_from_scale_rot
+
+    s = synthetic.make_scene(3000, "object", "sh1", -3.6, seed=21)
+    cov = cov3d_from_scale_rot(s.scales, s.rotations).to(DEV)
+    scene, cam = s.to(DEV), synthetic.orbit_camera(160, 90, 0.4).to(DEV)
+    bg = torch.zeros(3, device=DEV)
+    Wc, Wd = (t.to(DEV) for t in synthetic.loss_weights(160, 90))
+    _assert_stage_parity(pl.compare_stages(scene, cam, bg, cov3D=cov))
+    _assert_grad_parity(pl.compare_autograd(scene, cam, bg, Wc, Wd, cov3D=cov))
+
+
+def test_full_size_1m_1080p_sh3_vs_reference_cuda():
+    """BASELINE.json's headline configuration (config C)."""
+    _ref_or_skip()
+    scene = synthetic.config_scene("C").to(DEV)
+    cam = synthetic.config_cameras("C")[0].to(DEV)
+    bg = torch.zeros(3, device=DEV)
+    Wc, Wd = (t.to(DEV) for t in synthetic.loss_weights(cam.image_width, cam.image_height))
+    _assert_stage_parity(pl.compare_stages(scene, cam, bg))
+    _assert_grad_parity(pl.compare_autograd(scene, cam, bg, Wc, Wd))
+
+
+def test_edge_cases_vs_reference_cuda():
+    ref = _ref_or_skip()
+    mine = pl.ours()
+    bg = torch.tensor([0.3, 0.6, 0.9], device=DEV)
+    # P == 0: zero image, background NOT composited (rasterize_points.cu:68-82)
+    s0 = synthetic.make_scene(0, "object", "precomp", -3.0).to(DEV)
+    cam = synthetic.orbit_camera(48, 32, 0.0).to(DEV)
+    for api in (mine, ref):
+        R, color, depth, radii, *_ = api._C.rasterize_gaussians(*pl.forward_args(s0, cam, bg))
+        assert R == 0 and not color.any() and not depth.any() and radii.numel() == 0
+    # everything behind the camera: R == 0 but the blend still runs -> image == background
+    s = synthetic.make_scene(500, "object", "precomp", -3.0, seed=1)
+    s.means3D[:, 2] -= 10.0
+    s = s.to(DEV)
+    rep = pl.compare_stages(s, cam, bg)
+    assert rep["R_ours"] == 0 and rep["R_ref"] == 0 and rep["radii_mismatch"] == 0
+    R, color, depth, radii, *_ = mine._C.rasterize_gaussians(*pl.forward_args(s, cam, bg))
+    assert torch.allclose(color, bg.view(3, 1, 1).expand_as(color)) and not depth.any() and not radii.any()
+    Wc, Wd = (t.to(DEV) for t in synthetic.loss_weights(48, 32))
+    out = pl.run_autograd(mine, s, cam, bg, Wc, Wd)
+    assert all(not g.any() for g in out["grads"].values() if g is not None)
+    # a huge opaque Gaussian over the whole screen + saturation (0.99 clamp, T < 1e-4 early stop)
+    s = synthetic.make_scene(800, "object", "sh0", -3.0, seed=7)
+    s.scales[0] = torch.tensor([0.8, 0.8, 0.8])
+    s.means3D[0] = torch.tensor([0.0, 0.0, -1.5])
+    s.opacities[:100] = 1.0
+    s = s.to(DEV)
+    _assert_stage_parity(pl.compare_stages(s, cam, bg))
+    _assert_grad_parity(pl.compare_autograd(s, cam, bg, Wc, Wd))
+    # exact depth ties (duplicated Gaussians): stability of the sort decides the order
+    b = synthetic.make_scene(400, "object", "sh2", -3.0, seed=6)
+    dup = synthetic.Scene(*[None if t is None else torch.cat([t, t]).contiguous() for t in
+                            (b.means3D, b.scales, b.rotations, b.opacities, b.shs, b.colors_precomp)], b.sh_degree).to(DEV)
+    _assert_stage_parity(pl.compare_stages(dup, cam, bg))
+    # opacity below 1/255 and above 1: culling boxes must stay conservative
+    s = synthetic.make_scene(2000, "object", "precomp", -3.2, seed=8)
+    s.opacities[::3] = 0.003
+    s.opacities[1::3] = 1.7
+    s = s.to(DEV)
+    _assert_stage_parity(pl.compare_stages(s, cam, bg))
+    _assert_grad_parity(pl.compare_autograd(s, cam, bg, Wc, Wd))
+    # strongly anisotropic Gaussians (needle-like): loose fp32 power evaluation in the reference
+    s = synthetic.make_scene(1500, "object", "precomp", -4.0, seed=9)
+    s.scales[:, 0] *= 60.0
+    s = s.to(DEV)
+    _assert_stage_parity(pl.compare_stages(s, synthetic.orbit_camera(320, 200, 0.9).to(DEV), bg))
+
+
+def test_debug_flag_and_python_api_shapes():
+    mine = pl.ours()
+    scene = synthetic.make_scene(2000, "object", "sh3", -3.5, seed=2).to(DEV)
+    cam = synthetic.orbit_camera(96, 64, 0.1).to(DEV)
+    bg = torch.zeros(3, device=DEV)
+    a = mine._C.rasterize_gaussians(*pl.forward_args(scene, cam, bg, debug=False))
+    b = mine._C.rasterize_gaussians(*pl.forward_args(scene, cam, bg, debug=True))
+    assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert a[1].shape == (3, 64, 96) and a[2].shape == (1, 64, 96) and a[3].dtype == torch.int32
+
+
+def test_visible_filter_and_mark_visible():
+    ref = _ref_or_skip()
+    mine = pl.ours()
+    from bloomscene_b200.rasterizer import GaussianRasterizationSettings as S
+
+    scene = synthetic.make_scene(50_000, "band", "precomp", -3.5, seed=4).to(DEV)
+    cam = synthetic.yaw_camera(256, 192, 1.0).to(DEV)
+    st = synthetic.raster_settings(cam, 0, torch.zeros(3, device=DEV), S)
+    six = torch.cat([scene.scales, scene.scales * 2], dim=1)  # BloomScene passes scaling[:, :3] of a [P,6] tensor
+    sliced = six[:, :3]
+    assert not sliced.is_contiguous()
+    r_mine = mine.GaussianRasterizer(st).visible_filter(scene.means3D, sliced, scene.rotations)
+    r_ref = ref.GaussianRasterizer(st).visible_filter(scene.means3D, sliced, scene.rotations)
+    assert r_mine.dtype == torch.int32 and torch.equal(r_mine, r_ref)
+    fw = mine._C.rasterize_gaussians(*pl.forward_args(scene, cam, torch.zeros(3, device=DEV)))
+    assert torch.equal(fw[3], r_mine)
+    v_mine = mine.GaussianRasterizer(st).markVisible(scene.means3D)
+    v_ref = ref.GaussianRasterizer(st).markVisible(scene.means3D)
+    assert v_mine.dtype == torch.bool and torch.equal(v_mine, v_ref)
+    assert (v_mine | (r_mine == 0)).all()
+
+
+def test_sort_pairs_is_a_stable_radix_sort():
+    from bloomscene_b200 import _C
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for n, hi in [(0, 32), (1, 32), (33, 32), (4096, 9), (4097, 32), (123_457, 13), (1_000_003, 32), (3_000_000, 15)]:
+        keys = torch.randint(0, 2 ** 31 - 1, (n,), generator=g, dtype=torch.int64)
+        if hi < 32:
+            keys &= (1 << hi) - 1
+        if n > 100:
+            keys[::5] = keys[0]  # many exact ties
+        ko, vo = _C.sort_pairs(keys.to(torch.int32).to(DEV), None, 0, hi)
+        rk, ri = torch.sort(keys.to(DEV), stable=True)
+        assert torch.equal(ko.long(), rk) and torch.equal(vo.long(), ri), (n, hi)
+    # explicit values and a bit sub-range: order inside equal digits must be the input order
+    keys = torch.randint(0, 2 ** 20, (50_000,), generator=g, dtype=torch.int64)
+    vals = torch.randint(0, 2 ** 31 - 1, (50_000,), generator=g, dtype=torch.int64)
+    ko, vo = _C.sort_pairs(keys.to(torch.int32).to(DEV), vals.to(torch.int32).to(DEV), 4, 12)
+    digit = (keys >> 4) & 0xFF
+    _, ri = torch.sort(digit.to(DEV), stable=True)
+    assert torch.equal(vo.long(), vals.to(DEV)[ri]) and torch.equal(ko.long(), keys.to(DEV)[ri])
+
+
+def test_properties_at_full_size():
+    """Size-independent invariants at config C (1M Gaussians, 1080p, SH3) — no reference needed."""
+    from bloomscene_b200.debug import state_views
+
+    mine = pl.ours()
+    scene = synthetic.config_scene("C").to(DEV)
+    cam = synthetic.config_cameras("C")[0].to(DEV)
+    W, H = cam.image_width, cam.image_height
+    bg0 = torch.zeros(3, device=DEV)
+    R, color, depth, radii, geom, binning, img = mine._C.rasterize_gaussians(*pl.forward_args(scene, cam, bg0))
+    sv = state_views(mine._C, geom, binning, img, scene.P, R, W, H)
+    # ranges partition [0, R) in tile order; keys sorted by (tile, depth bits, id)
+    ranges = sv["ranges"].long()
+    nonempty = ranges[:, 1] > ranges[:, 0]
+    rs = ranges[nonempty]
+    assert rs[0, 0] == 0 and rs[-1, 1] == R and torch.equal(rs[1:, 0], rs[:-1, 1])
+    tile_of = torch.repeat_interleave(torch.arange(ranges.shape[0], device=DEV), (ranges[:, 1] - ranges[:, 0]).clamp(min=0))
+    pl_ids = sv["point_list"].long()
+    dk = sv["depth_key"].long() & 0xFFFFFFFF
+    keys = (tile_of << 32) | dk[pl_ids]
+    assert (keys[1:] >= keys[:-1]).all()
+    ties = keys[1:] == keys[:-1]
+    assert (pl_ids[1:][ties] > pl_ids[:-1][ties]).all()  # stable: ties keep Gaussian-id order
+    # every instance lies inside its Gaussian's tile rectangle; R == sum of rectangle areas
+    rect = sv["rect"]
+    x0, x1, y0, y1 = rect[:, 0] & 0xFFFF, rect[:, 0] >> 16, rect[:, 1] & 0xFFFF, rect[:, 1] >> 16
+    assert int(((x1 - x0) * (y1 - y0)).sum()) == R
+    gx = (W + 15) // 16
+    tx, ty = tile_of % gx, tile_of // gx
+    assert ((tx >= x0[pl_ids]) & (tx < x1[pl_ids]) & (ty >= y0[pl_ids]) & (ty < y1[pl_ids])).all()
+    assert ((radii > 0) == (sv["depth_key"] != -1)).all()
+    # n_contrib never exceeds the tile's list length; outputs are finite
+    n_contrib = sv["n_contrib"].view(H, W)
+    lens = (ranges[:, 1] - ranges[:, 0]).view((H + 15) // 16, gx)
+    per_pix = lens.repeat_interleave(16, 0)[:H].repeat_interleave(16, 1)[:, :W]
+    assert (n_contrib <= per_pix).all()
+    assert torch.isfinite(color).all() and torch.isfinite(depth).all() and (depth >= 0).all()
+    # determinism of every integer output and of the image across calls
+    R2, color2, depth2, radii2, geom2, binning2, img2 = mine._C.rasterize_gaussians(*pl.forward_args(scene, cam, bg0))
+    sv2 = state_views(mine._C, geom2, binning2, img2, scene.P, R2, W, H)
+    assert R2 == R and torch.equal(radii, radii2) and torch.equal(sv["point_list"], sv2["point_list"])
+    assert torch.equal(color, color2) and torch.equal(depth, depth2)
+    # background linearity: color(bg) - color(0) == final_T * bg
+    bg1 = torch.tensor([0.25, 0.5, 1.0], device=DEV)
+    _, color_bg, depth_bg, *_ = mine._C.rasterize_gaussians(*pl.forward_args(scene, cam, bg1))
+    T = sv["final_T"].view(1, H, W)
+    assert torch.allclose(color_bg - color, T * bg1.view(3, 1, 1), atol=2e-6)
+    assert torch.equal(depth_bg, depth)
+    # gradients: linear in dL/dpixel (2x upstream gradient -> 2x every gradient, exactly in fp32 up to atomics order)
+    Wc, Wd = (t.to(DEV) for t in synthetic.loss_weights(W, H))
+    g1 = pl.run_autograd(mine, scene, cam, bg0, Wc, Wd)["grads"]
+    g2 = pl.run_autograd(mine, scene, cam, bg0, 2 * Wc, Wd)["grads"]
+    for k in g1:
+        assert pl.rel_l2(g2[k], 2 * g1[k]) <= 1e-5, k
+
+
+def test_small_scene_vs_cpu_oracle():
+    from oracle import oracle as orc
+
+    mine = pl.ours()
+    scene_cpu = synthetic.make_scene(4000, "object", "sh2", -3.4, seed=12)
+    cam_cpu = synthetic.orbit_camera(150, 100, 0.8)
+    bg = torch.tensor([0.1, 0.3, 0.5])
+    Wc, Wd = synthetic.loss_weights(150, 100)
+    o = orc.run_scene(scene_cpu, cam_cpu, bg, dL_dcolor=Wc)
+    out = pl.run_autograd(mine, scene_cpu.to(DEV), cam_cpu.to(DEV), bg.to(DEV), Wc.to(DEV), Wd.to(DEV))
+    assert (out["radii"].cpu().numpy() != o["radii"]).mean() <= 1e-3
+    assert np.abs(out["color"].cpu().numpy() - o["color"]).max() <= 1e-4
+    assert np.abs(out["depth"].cpu().numpy() - o["depth"]).max() <= 1e-4
+    m = {"means3D": "dL_dmeans3D", "means2D": "dL_dmeans2D", "opacities": "dL_dopacity", "scales": "dL_dscales",
+         "rotations": "dL_drotations", "shs": "dL_dsh"}
+    for k, v in m.items():
+        assert pl.rel_l2(out["grads"][k].cpu(), torch.from_numpy(o["grads"][v])) <= 1e-3, k

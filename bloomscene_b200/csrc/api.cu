@@ -468,9 +468,11 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 		char* sort_scratch = scratch2 + 3 * rb;
 		char* emit_scratch = sort_scratch + sort_scratch_bytes(R);
 
-		BRS_STAGE(BRS_STAGE_EMIT, launch_emit(order, rect, (size_t)P, grid_x, inst_keys, inst_ids, (size_t)R, emit_scratch, stream), debug,
+		BRS_STAGE(BRS_STAGE_EMIT,
+		          launch_emit(order, rect, (size_t)P, grid_x, inst_keys, inst_ids, (size_t)R, emit_scratch, stream), debug,
 		          stream);
-		BRS_STAGE(BRS_STAGE_TILE_SORT, sort_pairs(inst_keys, inst_ids, sorted_keys, point_list, (size_t)R, 0, tile_bits(grid_x * grid_y),
+		BRS_STAGE(BRS_STAGE_TILE_SORT,
+		          sort_pairs(inst_keys, inst_ids, sorted_keys, point_list, (size_t)R, 0, tile_bits(grid_x * grid_y),
 		                     sort_scratch, stream),
 		          debug, stream);
 		BRS_STAGE(BRS_STAGE_TILE_RANGES, launch_tile_ranges(sorted_keys, (size_t)R, ranges, stream), debug, stream);

@@ -6,19 +6,24 @@
 // reference's emission order yields — is produced here with ~4x less memory traffic by splitting it:
 //
 //   1. stable sort of the P Gaussians by depth bits (u32 key, value = id; culled ones carry the
-//      key 0xFFFFFFFF and sink to the end)                                     -> `order`
-//   2. one fused kernel: exclusive scan of tiles-per-Gaussian in depth order (decoupled look-back)
-//      + emission of (tile id, Gaussian id) instances                           -> R pairs of 8 B
+//      key 0xFFFFFFFF, emit nothing, and may land anywhere)                    -> `order`
+//   2. one fused kernel: exclusive scan of tiles-per-Gaussian in depth order (decoupled look-back,
+//      32 predecessors per poll) + emission of (tile id, Gaussian id) instances
 //   3. stable sort of the instances by tile id only (ceil(log2(#tiles)) bits: 2 passes at 1080p)
 //   4. tile ranges from the sorted tile ids (reference identifyTileRanges, rasterizer_impl.cu:116-138)
 //
 // Because (1) is stable in id and (3) is stable, instances inside a tile end up ordered by
 // (depth bits, id): exactly the reference's sorted `point_list`.
 //
-// The sort itself is a hand-written onesweep: one upfront digit histogram per pass, then ONE kernel
-// per digit that ranks with warp match_any, resolves cross-tile offsets by chained decoupled
-// look-back (tiles take tickets from an atomic counter so predecessors are always resident), and
-// scatters through shared memory so global writes are coalesced per digit run.
+// The radix sort is hand-written.  Each pass over one digit is three kernels:
+//   upsweep   : per 4096-key tile, digit counts (warp match_any + shared atomics)  -> table[digit][tile]
+//   scan      : one block per digit, exclusive scan along the tiles + digit totals
+//   downsweep : per tile, stable ranks (match_any + shared atomics returning the old value, so the
+//               16 keys of a thread are in flight together), scatter through shared memory so
+//               global writes are coalesced per digit run.
+// A single-pass chained scan ("onesweep") was measured first: with ~600 tiles resident at once the
+// first wave spends ~100 us per pass polling unpublished predecessors on this GPU, far more than
+// the extra 4 bytes/key the upsweep reads (see profiles/).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -33,8 +38,8 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 pairs per tile
 constexpr int RADIX_MAX = 256;
 constexpr int MAX_PASSES = 4;
 
-constexpr uint32_t FLAG_LOCAL = 1u << 30; // tile-local count published
-constexpr uint32_t FLAG_INCL = 2u << 30;  // inclusive prefix published
+constexpr uint32_t FLAG_LOCAL = 1u << 30; // (emit scan) block-local count published
+constexpr uint32_t FLAG_INCL = 2u << 30;  // (emit scan) inclusive prefix published
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
 
@@ -77,74 +82,63 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 	return warp_off + incl - v;
 }
 
-struct PassPlan {
-	int passes;
-	int shift[MAX_PASSES];
-	int bits[MAX_PASSES];
-};
-
-PassPlan plan_passes(int begin_bit, int end_bit)
-{
-	PassPlan p{};
-	int nbits = end_bit - begin_bit;
-	if (nbits < 1)
-		nbits = 1;
-	p.passes = (nbits + 7) / 8;
-	int base = nbits / p.passes, extra = nbits % p.passes, s = begin_bit;
-	for (int i = 0; i < p.passes; i++) {
-		p.bits[i] = base + (i < extra ? 1 : 0);
-		p.shift[i] = s;
-		s += p.bits[i];
-	}
-	return p;
-}
-
-struct HistArgs {
-	int passes;
-	int shift[MAX_PASSES];
-	int bits[MAX_PASSES];
-};
-
-// One read of the keys -> digit histograms of every pass.  Warp-aggregated (match_any) shared
-// atomics, so degenerate digit distributions (the top depth byte has ~5 values, neighbouring
-// instances share their tile's high digit) do not serialise.
-__global__ void __launch_bounds__(SORT_THREADS) histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n,
-                                                                HistArgs h, uint32_t* __restrict__ hist)
-{
-	__shared__ uint32_t s_hist[MAX_PASSES][RADIX_MAX];
-	for (int i = threadIdx.x; i < MAX_PASSES * RADIX_MAX; i += SORT_THREADS)
-		(&s_hist[0][0])[i] = 0;
-	__syncthreads();
-	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t stride = gridDim.x * SORT_THREADS;
-	// n rounded up so whole warps stay converged for match_any
-	const uint32_t n_round = (n + 31u) & ~31u;
-	for (uint32_t i = blockIdx.x * SORT_THREADS + threadIdx.x; i < n_round; i += stride) {
-		const bool valid = i < n;
-		const uint32_t key = valid ? __ldg(keys + i) : 0u;
-#pragma unroll
-		for (int p = 0; p < MAX_PASSES; p++) {
-			if (p < h.passes) {
-				const uint32_t d = (key >> h.shift[p]) & ((1u << h.bits[p]) - 1u);
-				const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
-				if (valid && (uint32_t)(__ffs(peers) - 1) == lane)
-					atomicAdd(&s_hist[p][d], (uint32_t)__popc(peers));
-			}
-		}
-	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < h.passes * RADIX_MAX; i += SORT_THREADS) {
-		const uint32_t c = (&s_hist[0][0])[i];
-		if (c)
-			atomicAdd(hist + i, c);
-	}
-}
-
-// One stable counting-sort pass over digit (key >> shift) & mask.
+// ---- upsweep: digit counts of one tile ------------------------------------------------------------
 __global__ void __launch_bounds__(SORT_THREADS)
-    onesweep_pass_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                         uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, uint32_t n, int shift, int bits,
-                         const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket)
+    upsweep_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, int bits, uint32_t tiles,
+                   uint32_t* __restrict__ table)
+{
+	__shared__ uint32_t s_cnt[RADIX_MAX];
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	const uint32_t radix = 1u << bits, mask = radix - 1u;
+	s_cnt[tid] = 0;
+	__syncthreads();
+	const uint32_t tile = blockIdx.x;
+	const uint32_t base = tile * SORT_TILE;
+	const uint32_t valid_count = min((uint32_t)SORT_TILE, n - base);
+	uint32_t key[SORT_ITEMS];
+#pragma unroll
+	for (int i = 0; i < SORT_ITEMS; i++) {
+		const uint32_t li = tid + i * SORT_THREADS;
+		key[i] = (li < valid_count) ? __ldg(keys + base + li) : 0xffffffffu;
+	}
+#pragma unroll
+	for (int i = 0; i < SORT_ITEMS; i++) {
+		const bool valid = (tid + i * SORT_THREADS) < valid_count;
+		const uint32_t d = (key[i] >> shift) & mask;
+		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
+		if (valid && (uint32_t)(__ffs(peers) - 1) == lane)
+			atomicAdd(s_cnt + d, (uint32_t)__popc(peers));
+	}
+	__syncthreads();
+	if (tid < radix)
+		table[(size_t)tid * tiles + tile] = s_cnt[tid];
+}
+
+// ---- scan: per digit, exclusive prefix over the tiles (in place) + digit total --------------------
+__global__ void __launch_bounds__(SORT_THREADS) scan_kernel(uint32_t* __restrict__ table, uint32_t tiles,
+                                                           uint32_t* __restrict__ totals)
+{
+	__shared__ uint32_t s_warp[SORT_WARPS];
+	uint32_t* row = table + (size_t)blockIdx.x * tiles;
+	uint32_t carry = 0;
+	for (uint32_t t0 = 0; t0 < tiles; t0 += SORT_THREADS) {
+		const uint32_t t = t0 + threadIdx.x;
+		const uint32_t v = (t < tiles) ? row[t] : 0u;
+		uint32_t total;
+		const uint32_t ex = block_exclusive_scan_256(v, s_warp, total);
+		if (t < tiles)
+			row[t] = carry + ex;
+		carry += total;
+	}
+	if (threadIdx.x == 0)
+		totals[blockIdx.x] = carry;
+}
+
+// ---- downsweep: stable scatter of one tile --------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS)
+    downsweep_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint32_t* __restrict__ kout,
+                     uint32_t* __restrict__ vout, uint32_t n, int shift, int bits, uint32_t tiles,
+                     const uint32_t* __restrict__ table, const uint32_t* __restrict__ totals)
 {
 	__shared__ uint32_t s_cnt[SORT_WARPS][RADIX_MAX];
 	__shared__ uint32_t s_keys[SORT_TILE];
@@ -152,54 +146,48 @@ __global__ void __launch_bounds__(SORT_THREADS)
 	__shared__ uint32_t s_digit_start[RADIX_MAX];
 	__shared__ uint32_t s_goff[RADIX_MAX];
 	__shared__ uint32_t s_warp[SORT_WARPS];
-	__shared__ uint32_t s_tile;
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t radix = 1u << bits, mask = radix - 1u;
-
-	if (tid == 0)
-		s_tile = atomicAdd(ticket, 1u);
 	for (int i = tid; i < SORT_WARPS * RADIX_MAX; i += SORT_THREADS)
 		(&s_cnt[0][0])[i] = 0;
 	__syncthreads();
-	const uint32_t tile = s_tile;
+	const uint32_t tile = blockIdx.x;
 	const uint32_t base = tile * SORT_TILE;
 	const uint32_t valid_count = min((uint32_t)SORT_TILE, n - base);
 
-	// ---- load (warp-striped: coalesced, and rank order == index order) ----
-	uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+	// load keys (warp-striped: coalesced, and rank order == index order)
+	uint32_t key[SORT_ITEMS], rank[SORT_ITEMS];
 	const uint32_t wbase = warp * (32 * SORT_ITEMS) + lane;
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
 		const uint32_t li = wbase + i * 32;
-		const bool valid = li < valid_count;
-		key[i] = valid ? __ldg(kin + base + li) : 0xffffffffu;
-		val[i] = valid ? (vin ? __ldg(vin + base + li) : base + li) : 0u;
+		key[i] = (li < valid_count) ? __ldg(kin + base + li) : 0xffffffffu;
 	}
+	// global offsets of this tile's digits (independent of the ranking below)
+	const uint32_t tile_excl = (tid < radix) ? __ldg(table + (size_t)tid * tiles + tile) : 0u;
+	const uint32_t digit_total = (tid < radix) ? __ldg(totals + tid) : 0u;
 
-	// ---- rank inside the warp (stable): match_any groups equal digits, the group's first lane
-	//      bumps the warp-private counter ----
+	// rank inside the warp (stable).  match_any groups equal digits; the group's first lane bumps the
+	// warp-private counter with a shared-memory atomic that returns the old value.  Same-address
+	// atomics of one warp complete in program order, so no barrier is needed and all SORT_ITEMS
+	// chains (MATCH -> ATOMS -> SHFL) overlap.
+	uint32_t* my_cnt = s_cnt[warp];
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
 		const bool valid = (wbase + i * 32) < valid_count;
 		const uint32_t d = (key[i] >> shift) & mask;
 		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
-		rank[i] = 0;
-		if (valid) {
-			const int leader = __ffs(peers) - 1;
-			uint32_t old = 0;
-			if ((int)lane == leader) {
-				old = s_cnt[warp][d];
-				s_cnt[warp][d] = old + __popc(peers);
-			}
-			old = __shfl_sync(peers, old, leader);
-			rank[i] = old + __popc(peers & lanemask_lt());
-		}
-		__syncwarp();
+		const int leader = __ffs(peers) - 1;
+		uint32_t old = 0;
+		if (valid && (int)lane == leader)
+			old = atomicAdd(my_cnt + d, (uint32_t)__popc(peers));
+		old = __shfl_sync(0xffffffffu, old, leader);
+		rank[i] = old + __popc(peers & lanemask_lt());
 	}
 	__syncthreads();
 
-	// ---- per digit: exclusive offsets of the warps, tile total ----
+	// per digit: exclusive offsets of the warps, tile total
 	uint32_t total = 0;
 	if (tid < radix) {
 #pragma unroll
@@ -208,50 +196,30 @@ __global__ void __launch_bounds__(SORT_THREADS)
 			s_cnt[w][tid] = total;
 			total += c;
 		}
-		// publish before anything else so successors can make progress
-		st_relaxed(status + (size_t)tile * RADIX_MAX + tid, (tile == 0 ? FLAG_INCL : FLAG_LOCAL) | total);
 	}
-
-	// ---- where each digit starts inside this tile / inside the whole array ----
 	uint32_t dummy;
 	const uint32_t digit_start = block_exclusive_scan_256(total, s_warp, dummy);
-	const uint32_t bin_base = block_exclusive_scan_256(tid < radix ? __ldg(hist + tid) : 0u, s_warp, dummy);
-
-	// ---- decoupled look-back: sum of this digit's counts over all earlier tiles ----
+	const uint32_t bin_base = block_exclusive_scan_256(digit_total, s_warp, dummy);
 	if (tid < radix) {
-		uint32_t excl = 0;
-		if (tile > 0) {
-			int p = (int)tile - 1;
-			while (true) {
-				const uint32_t v = ld_relaxed(status + (size_t)p * RADIX_MAX + tid);
-				const uint32_t f = v & FLAG_MASK;
-				if (f == 0)
-					continue; // predecessor has not published yet
-				excl += v & VALUE_MASK;
-				if (f == FLAG_INCL)
-					break;
-				p--;
-			}
-			st_relaxed(status + (size_t)tile * RADIX_MAX + tid, FLAG_INCL | (excl + total));
-		}
 		s_digit_start[tid] = digit_start;
-		s_goff[tid] = bin_base + excl - digit_start; // global position = s_goff[d] + position in tile
+		s_goff[tid] = bin_base + tile_excl - digit_start; // global position = s_goff[d] + position in tile
 	}
 	__syncthreads();
 
-	// ---- scatter into shared memory in sorted-by-digit order ----
+	// scatter into shared memory in sorted-by-digit order (values are fetched only now)
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
-		if ((wbase + i * 32) < valid_count) {
+		const uint32_t li = wbase + i * 32;
+		if (li < valid_count) {
 			const uint32_t d = (key[i] >> shift) & mask;
 			const uint32_t pos = s_digit_start[d] + s_cnt[warp][d] + rank[i];
 			s_keys[pos] = key[i];
-			s_vals[pos] = val[i];
+			s_vals[pos] = vin ? __ldg(vin + base + li) : base + li;
 		}
 	}
 	__syncthreads();
 
-	// ---- coalesced write-out: consecutive threads hold consecutive positions of a digit run ----
+	// coalesced write-out: consecutive threads hold consecutive positions of a digit run
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
 		const uint32_t j = tid + i * SORT_THREADS;
@@ -265,12 +233,10 @@ __global__ void __launch_bounds__(SORT_THREADS)
 }
 
 struct SortScratch {
-	uint32_t* hist;   // [MAX_PASSES][RADIX_MAX]
-	uint32_t* ticket; // [MAX_PASSES] (+ padding)
-	uint32_t* status; // [MAX_PASSES][tiles][RADIX_MAX]
+	uint32_t* table;  // [RADIX_MAX][tiles] (reused by every pass)
+	uint32_t* totals; // [RADIX_MAX]
 	uint32_t* tmp_keys;
 	uint32_t* tmp_vals;
-	size_t zero_bytes; // prefix of the scratch that must be zero before sorting
 	size_t total_bytes;
 };
 
@@ -280,13 +246,10 @@ SortScratch carve_sort_scratch(void* scratch, size_t n)
 	const size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
 	char* p = static_cast<char*>(scratch);
 	size_t off = 0;
-	s.hist = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * MAX_PASSES * RADIX_MAX, 256);
-	s.ticket = reinterpret_cast<uint32_t*>(p + off);
-	off += 256;
-	s.status = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * MAX_PASSES * tiles * RADIX_MAX, 256);
-	s.zero_bytes = off;
+	s.table = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * RADIX_MAX * (tiles ? tiles : 1), 256);
+	s.totals = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * RADIX_MAX, 256);
 	s.tmp_keys = reinterpret_cast<uint32_t*>(p + off);
 	off += align_up(sizeof(uint32_t) * n, 256);
 	s.tmp_vals = reinterpret_cast<uint32_t*>(p + off);
@@ -304,44 +267,36 @@ cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_
 {
 	if (n == 0)
 		return cudaSuccess;
-	const PassPlan plan = plan_passes(begin_bit, end_bit);
+	int nbits = end_bit - begin_bit;
+	if (nbits < 1)
+		nbits = 1;
+	const int passes = (nbits + 7) / 8;
+	const int base_bits = nbits / passes, extra = nbits % passes;
 	SortScratch s = carve_sort_scratch(scratch, n);
 	const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
-	cudaError_t e = cudaMemsetAsync(scratch, 0, s.zero_bytes, stream);
-	if (e != cudaSuccess)
-		return e;
-
-	HistArgs h{};
-	h.passes = plan.passes;
-	for (int i = 0; i < plan.passes; i++) {
-		h.shift[i] = plan.shift[i];
-		h.bits[i] = plan.bits[i];
-	}
-	size_t hist_blocks_sz = (n + SORT_THREADS * 8 - 1) / (SORT_THREADS * 8);
-	if (hist_blocks_sz > 148 * 4)
-		hist_blocks_sz = 148 * 4;
-	const uint32_t hist_blocks = (uint32_t)hist_blocks_sz;
-	histogram_kernel<<<hist_blocks, SORT_THREADS, 0, stream>>>(keys_in, (uint32_t)n, h, s.hist);
-	count_launch();
-
 	const uint32_t* kin = keys_in;
 	const uint32_t* vin = vals_in;
-	for (int p = 0; p < plan.passes; p++) {
-		const bool to_out = ((plan.passes - 1 - p) & 1) == 0;
+	int shift = begin_bit;
+	for (int p = 0; p < passes; p++) {
+		const int bits = base_bits + (p < extra ? 1 : 0);
+		const bool to_out = ((passes - 1 - p) & 1) == 0;
 		uint32_t* ko = to_out ? keys_out : s.tmp_keys;
 		uint32_t* vo = to_out ? vals_out : s.tmp_vals;
-		onesweep_pass_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, ko, vo, (uint32_t)n, plan.shift[p],
-		                                                         plan.bits[p], s.hist + p * RADIX_MAX,
-		                                                         s.status + (size_t)p * tiles * RADIX_MAX,
-		                                                         s.ticket + p);
+		upsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, (uint32_t)n, shift, bits, tiles, s.table);
+		scan_kernel<<<1u << bits, SORT_THREADS, 0, stream>>>(s.table, tiles, s.totals);
+		downsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, ko, vo, (uint32_t)n, shift, bits, tiles, s.table,
+		                                                     s.totals);
+		count_launch();
+		count_launch();
 		count_launch();
 		kin = ko;
 		vin = vo;
+		shift += bits;
 	}
 	return cudaGetLastError();
 }
 
-// ---- fused scan + emission ----------------------------------------------------------------------
+// ---- fused scan + emission ------------------------------------------------------------------------
 
 namespace {
 
@@ -360,7 +315,7 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 	__shared__ uint32_t s_warp[SORT_WARPS];
 	__shared__ uint32_t s_bcast[2];
 
-	const uint32_t tid = threadIdx.x;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0)
 		s_bcast[0] = atomicAdd(ticket, 1u);
 	__syncthreads();
@@ -379,8 +334,8 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 			r = __ldg(rect + id);
 		}
 		const uint32_t w = (r.x >> 16) - (r.x & 0xffffu);
-		const uint32_t h = (r.y >> 16) - (r.y & 0xffffu);
-		cnt[k] = w * h;
+		const uint32_t hgt = (r.y >> 16) - (r.y & 0xffffu);
+		cnt[k] = w * hgt;
 		tsum += cnt[k];
 		s_id[tid * EMIT_ITEMS + k] = id;
 		s_rect[tid * EMIT_ITEMS + k] = r;
@@ -393,27 +348,36 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 		s_incl[tid * EMIT_ITEMS + k] = run;
 	}
 
-	// chained scan over blocks (single value): decoupled look-back
-	if (tid == 0) {
+	// chained scan over blocks (single value): decoupled look-back by the whole first warp,
+	// 32 predecessors per poll
+	if (warp == 0) {
+		if (lane == 0)
+			st_relaxed(status + blk, (blk == 0 ? FLAG_INCL : FLAG_LOCAL) | block_total);
 		uint32_t excl = 0;
-		if (blk == 0) {
-			st_relaxed(status, FLAG_INCL | block_total);
-		} else {
-			st_relaxed(status + blk, FLAG_LOCAL | block_total);
-			int p = (int)blk - 1;
-			while (true) {
-				const uint32_t v = ld_relaxed(status + p);
-				const uint32_t f = v & FLAG_MASK;
-				if (f == 0)
-					continue;
-				excl += v & VALUE_MASK;
-				if (f == FLAG_INCL)
-					break;
-				p--;
-			}
-			st_relaxed(status + blk, FLAG_INCL | (excl + block_total));
+		int p = (int)blk - 1;
+		while (p >= 0) {
+			const int q = p - (int)lane;
+			const uint32_t v = (q >= 0) ? ld_relaxed(status + q) : FLAG_INCL;
+			const uint32_t f = v & FLAG_MASK;
+			const uint32_t not_ready = __ballot_sync(0xffffffffu, f == 0);
+			const uint32_t inclusive = __ballot_sync(0xffffffffu, f == FLAG_INCL);
+			const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+			const int first_in = inclusive ? __ffs(inclusive) - 1 : 32;
+			const int take = (first_in < first_nr) ? first_in + 1 : first_nr; // lanes [0, take) are summed
+			uint32_t c = ((int)lane < take) ? (v & VALUE_MASK) : 0u;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				c += __shfl_xor_sync(0xffffffffu, c, o);
+			excl += c;
+			if (first_in < first_nr)
+				break;
+			p -= first_nr;
 		}
-		s_bcast[1] = excl;
+		if (lane == 0) {
+			if (blk > 0)
+				st_relaxed(status + blk, FLAG_INCL | (excl + block_total));
+			s_bcast[1] = excl;
+		}
 	}
 	__syncthreads();
 	const uint32_t gbase = s_bcast[1];
@@ -430,12 +394,12 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 		}
 		const uint2 r = s_rect[lo];
 		const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
-		const uint32_t h = (r.y >> 16) - y0;
-		const uint32_t k = j - (s_incl[lo] - w * h);
-		const uint32_t ty = y0 + k / w, tx = x0 + (k - (k / w) * w);
+		const uint32_t hgt = (r.y >> 16) - y0;
+		const uint32_t k = j - (s_incl[lo] - w * hgt);
+		const uint32_t row = k / w;
 		const uint32_t g = gbase + j;
 		if (g < R) {
-			tile_keys[g] = ty * grid_x + tx;
+			tile_keys[g] = (y0 + row) * grid_x + x0 + (k - row * w);
 			inst_ids[g] = s_id[lo];
 		}
 	}

@@ -159,7 +159,10 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				for (int i = 0; i < 9; i++)
 					v[i] = 0.f;
 				if (ok) {
-					T = T / (1.f - alpha);
+					// 1 - alpha >= 0.01 (alpha is clamped to 0.99): one MUFU.RCP (<= 1 ulp) replaces the
+					// reference's two IEEE divisions; gradients are tolerance-checked (rel-L2 <= 1e-4)
+					const float rcp = __fdividef(1.0f, 1.f - alpha);
+					T = T * rcp;
 					const float dchannel_dcolor = alpha * T;
 
 					float dL_dalpha = 0.0f;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 					dL_dalpha += (col.z - accum_rec2) * dpx2;
 					dL_dalpha *= T;
 					last_alpha = alpha;
-					dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+					dL_dalpha += (-T_final * rcp) * bg_dot_dpixel;
 
 					const float dL_dG = con.w * dL_dalpha;
 					const float gdx = G * dx;

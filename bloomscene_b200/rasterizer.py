@@ -38,99 +38,66 @@ def cpu_deep_copy_tuple(input_tuple):
     return tuple(copied_tensors)
 
 
+def _absent() -> torch.Tensor:
+    """Placeholder for an optional input that was not given: an empty CPU tensor, whose data pointer is
+    NULL — the reference's own convention (reference __init__.py:198-208)."""
+    return torch.Tensor([])
+
+
+def _guarded(native_fn, args, debug: bool, dump_file: str, message: str):
+    """Call into the native module; with `debug` set, snapshot the arguments first and write them to
+    `dump_file` if the call raises (reference __init__.py:83-90 forward, :133-140 backward)."""
+    if not debug:
+        return native_fn(*args)
+    snapshot = cpu_deep_copy_tuple(args)  # taken before the call so a crash cannot corrupt it
+    try:
+        return native_fn(*args)
+    except Exception:
+        torch.save(snapshot, dump_file)
+        print(message)
+        raise
+
+
 def bind(_C) -> SimpleNamespace:
     """Create (rasterize_gaussians, _RasterizeGaussians, GaussianRasterizer) bound to native module `_C`."""
 
     class _RasterizeGaussians(torch.autograd.Function):
-        # reference __init__.py:44-156
+        """Autograd node around _C.rasterize_gaussians / _C.rasterize_gaussians_backward; argument orders
+        are those of the binding (reference __init__.py:53-73 forward, :108-131 backward)."""
+
         @staticmethod
         def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                     raster_settings):
-            args = (
-                raster_settings.bg,
-                means3D,
-                colors_precomp,
-                opacities,
-                scales,
-                rotations,
-                raster_settings.scale_modifier,
-                cov3Ds_precomp,
-                raster_settings.viewmatrix,
-                raster_settings.projmatrix,
-                raster_settings.tanfovx,
-                raster_settings.tanfovy,
-                raster_settings.image_height,
-                raster_settings.image_width,
-                sh,
-                raster_settings.sh_degree,
-                raster_settings.campos,
-                raster_settings.prefiltered,
-                raster_settings.debug,
-            )
-            if raster_settings.debug:
-                cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
-                try:
-                    num_rendered, color, depth, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
-                except Exception as ex:
-                    torch.save(cpu_args, "snapshot_fw.dump")
-                    print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
-                    raise ex
-            else:
-                num_rendered, color, depth, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
-
-            ctx.raster_settings = raster_settings
+            rs = raster_settings
+            out = _guarded(
+                _C.rasterize_gaussians,
+                (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
+                 rs.sh_degree, rs.campos, rs.prefiltered, rs.debug),
+                rs.debug, "snapshot_fw.dump",
+                "\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+            num_rendered, color, depth, radii, geom, binning, image = out
+            ctx.raster_settings = rs
             ctx.num_rendered = num_rendered
-            ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
-                                  binningBuffer, imgBuffer)
+            ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom,
+                                  binning, image)
             return color, radii, depth
 
         @staticmethod
         def backward(ctx, grad_out_color, grad_radii, grad_depth):
-            num_rendered = ctx.num_rendered
-            raster_settings = ctx.raster_settings
-            (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
-             imgBuffer) = ctx.saved_tensors
-
-            args = (
-                raster_settings.bg,
-                means3D,
-                radii,
-                colors_precomp,
-                scales,
-                rotations,
-                raster_settings.scale_modifier,
-                cov3Ds_precomp,
-                raster_settings.viewmatrix,
-                raster_settings.projmatrix,
-                raster_settings.tanfovx,
-                raster_settings.tanfovy,
-                grad_out_color,
-                grad_depth,
-                sh,
-                raster_settings.sh_degree,
-                raster_settings.campos,
-                geomBuffer,
-                num_rendered,
-                binningBuffer,
-                imgBuffer,
-                raster_settings.debug,
-            )
-            if raster_settings.debug:
-                cpu_args = cpu_deep_copy_tuple(args)
-                try:
-                    (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh,
-                     grad_scales, grad_rotations) = _C.rasterize_gaussians_backward(*args)
-                except Exception as ex:
-                    torch.save(cpu_args, "snapshot_bw.dump")
-                    print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
-                    raise ex
-            else:
-                (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh,
-                 grad_scales, grad_rotations) = _C.rasterize_gaussians_backward(*args)
-
-            # order of the autograd inputs (reference __init__.py:144-154); grad_radii / grad_depth carry nothing
-            return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales,
-                    grad_rotations, grad_cov3Ds_precomp, None)
+            rs = ctx.raster_settings
+            colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, image = ctx.saved_tensors
+            g = _guarded(
+                _C.rasterize_gaussians_backward,
+                (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, sh, rs.sh_degree,
+                 rs.campos, geom, ctx.num_rendered, binning, image, rs.debug),
+                rs.debug, "snapshot_bw.dump",
+                "\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+            d_means2D, d_colors, d_opacities, d_means3D, d_cov3D, d_sh, d_scales, d_rotations = g
+            # one gradient per autograd input, in input order (reference __init__.py:144-154);
+            # grad_radii carries nothing and grad_depth is plumbed down but unused by the kernels
+            return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None
 
     def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                             raster_settings):
@@ -139,59 +106,36 @@ def bind(_C) -> SimpleNamespace:
                                          cov3Ds_precomp, raster_settings)
 
     class GaussianRasterizer(nn.Module):
-        # reference __init__.py:172-249
+        """reference __init__.py:172-249: forward / visible_filter / markVisible with the same signatures."""
+
         def __init__(self, raster_settings):
             super().__init__()
             self.raster_settings = raster_settings
 
         def markVisible(self, positions):
+            rs = self.raster_settings
             with torch.no_grad():
-                raster_settings = self.raster_settings
-                visible = _C.mark_visible(positions, raster_settings.viewmatrix, raster_settings.projmatrix)
-            return visible
+                return _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
 
         def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                     cov3D_precomp=None):
-            raster_settings = self.raster_settings
-
-            if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            # same two checks and messages (typo included) as reference __init__.py:192-196
+            if (shs is None) == (colors_precomp is None):
                 raise Exception('Please provide excatly one of either SHs or precomputed colors!')
-
-            if ((scales is None or rotations is None) and cov3D_precomp is None) or (
-                    (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            has_any_sr, has_both_sr = (scales is not None or rotations is not None), (scales is not None and rotations is not None)
+            if (not has_both_sr and cov3D_precomp is None) or (has_any_sr and cov3D_precomp is not None):
                 raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
-
-            if shs is None:
-                shs = torch.Tensor([])
-            if colors_precomp is None:
-                colors_precomp = torch.Tensor([])
-            if scales is None:
-                scales = torch.Tensor([])
-            if rotations is None:
-                rotations = torch.Tensor([])
-            if cov3D_precomp is None:
-                cov3D_precomp = torch.Tensor([])
-
-            return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                       cov3D_precomp, raster_settings)
+            opt = lambda t: _absent() if t is None else t
+            return rasterize_gaussians(means3D, means2D, opt(shs), opt(colors_precomp), opacities, opt(scales),
+                                       opt(rotations), opt(cov3D_precomp), self.raster_settings)
 
         def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
-            raster_settings = self.raster_settings
-
-            if scales is None:
-                scales = torch.Tensor([])
-            if rotations is None:
-                rotations = torch.Tensor([])
-            if cov3D_precomp is None:
-                cov3D_precomp = torch.Tensor([])
-
+            rs = self.raster_settings
+            opt = lambda t: _absent() if t is None else t
             with torch.no_grad():
-                radii = _C.rasterize_aussians_filter(
-                    means3D, scales, rotations, raster_settings.scale_modifier, cov3D_precomp,
-                    raster_settings.viewmatrix, raster_settings.projmatrix, raster_settings.tanfovx,
-                    raster_settings.tanfovy, raster_settings.image_height, raster_settings.image_width,
-                    raster_settings.prefiltered, raster_settings.debug)
-            return radii
+                return _C.rasterize_aussians_filter(means3D, opt(scales), opt(rotations), rs.scale_modifier,
+                                                    opt(cov3D_precomp), rs.viewmatrix, rs.projmatrix, rs.tanfovx,
+                                                    rs.tanfovy, rs.image_height, rs.image_width, rs.prefiltered, rs.debug)
 
     return SimpleNamespace(
         _C=_C,

@@ -106,14 +106,15 @@ def get_api(impl: str):
     return bind(mod)
 
 
-def stage_model(P, V, R, M, npix, ntile, E, C, Eb):
-    """Algorithmic bytes / flops per view and stage."""
+def stage_model(P, V, R, R1, M, npix, ntile, E, C, Eb):
+    """Algorithmic bytes / flops per view and stage (binning stages as built).
+    R1 = (supertile, Gaussian) instances, the only thing the coarse level sorts."""
     return {
         "preprocess": ("hbm", 52 * P + (12 * M + 67) * V),
         "depth_sort": ("hbm", (4 + 16 * 4) * P),  # one histogram read + 4 passes reading and writing 8-byte pairs
-        "emit": ("hbm", 4 * P + 8 * V + 8 * R),
-        "tile_sort": ("hbm", (4 + 16 * 2) * R),  # histogram read + 2 passes of 8-byte pairs at 1080p
-        "tile_ranges": ("hbm", 4 * R + 8 * ntile),
+        "coarse_emit": ("hbm", 4 * P + 8 * V + 8 * R1),
+        "coarse_sort": ("hbm", (4 + 16) * R1),  # histogram read + one pass of 8-byte pairs (<= 256 supertiles)
+        "fine_bin": ("hbm", 2 * (4 + 8) * R1 + 4 * R + 16 * ntile),  # count + scatter passes read id + rect; ids written once
         "blend_fwd": ("fp32", 21 * E + 16 * C),
         "blend_bwd": ("fp32", 21 * Eb + 70 * C),
         "preprocess_bwd": ("hbm", 4 * P + 48 * P + (171 + 24 * M) * V),
@@ -310,7 +311,7 @@ def main():
         hbm_peak, hbm_src = measured_peaks()
         fp32_peak = api._C.probe_fp32_tflops()
         st = prof["stats"]
-        model = stage_model(cfg["P"], st["V"], st["R"], 16, W * H, ((W + 15) // 16) * ((H + 15) // 16), st["E"], st["C"], st["Eb"])
+        model = stage_model(cfg["P"], st["V"], st["R"], st["R1"], 16, W * H, ((W + 15) // 16) * ((H + 15) // 16), st["E"], st["C"], st["Eb"])
         stages = {}
         t_roof = 0.0
         for name, (bound, work) in model.items():

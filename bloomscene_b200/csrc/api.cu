@@ -4,10 +4,11 @@
 // sub-allocator (rasterizer_impl.h:21-73, rasterizer_impl.cu:155-194).
 //
 // Stage order of brs_forward (all on the caller's stream):
-//   memset(header, ranges) -> preprocess -> [async copy of R to pinned host memory + event]
-//   -> depth sort (hist + 4 onesweep passes; does not need R, so the GPU stays busy while the host
-//      waits for the event) -> host: wait R, allocate binning/scratch -> scan+emit -> tile sort
-//   (hist + 1..3 passes) -> tile ranges -> blend.
+//   memset(header) -> preprocess -> [async copy of R, R1 to pinned host memory + event]
+//   -> depth sort (4 radix passes over P keys; does not need R, so the GPU stays busy while the host
+//      waits for the event) -> host: wait R/R1, allocate binning/scratch -> coarse binning (scan +
+//      emit of supertile instances, one radix pass on the supertile id) -> fine binning (count, scan,
+//      scatter: point_list and tile ranges) -> blend.
 // brs_backward: memset(accumulator) -> blend backward -> fused preprocess backward.  No host sync.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -254,13 +255,16 @@ size_t brs_image_bytes(int W, int H) { return image_layout(W, H).total; }
 size_t brs_sort_scratch_bytes(int n) { return sort_scratch_bytes(n < 0 ? 0 : (size_t)n); }
 
 static size_t depth_scratch_bytes(size_t P) { return align_up(sizeof(uint32_t) * P, 256) + sort_scratch_bytes(P); }
-static size_t instance_scratch_bytes(size_t P, size_t R)
+// R1 = supertile instances (what the coarse level sorts); never more than the tile instances R.
+static size_t instance_scratch_bytes(size_t P, size_t R1, uint32_t grid_x, uint32_t grid_y)
 {
-	return 3 * align_up(sizeof(uint32_t) * R, 256) + sort_scratch_bytes(R) + emit_scratch_bytes(P);
+	return 4 * align_up(sizeof(uint32_t) * R1, 256) + sort_scratch_bytes(R1) + emit_scratch_bytes(P) +
+	       fine_scratch_bytes(R1, grid_x, grid_y);
 }
-size_t brs_forward_scratch_bytes(int P, int R, int, int)
+size_t brs_forward_scratch_bytes(int P, int R, int W, int H)
 {
-	return depth_scratch_bytes(P < 0 ? 0 : P) + instance_scratch_bytes(P < 0 ? 0 : P, R < 0 ? 0 : R);
+	const uint32_t gx = W > 0 ? (W + TILE_X - 1) / TILE_X : 0, gy = H > 0 ? (H + TILE_Y - 1) / TILE_Y : 0;
+	return depth_scratch_bytes(P < 0 ? 0 : P) + instance_scratch_bytes(P < 0 ? 0 : P, R < 0 ? 0 : R, gx, gy);
 }
 size_t brs_backward_scratch_bytes(int P) { return align_up(sizeof(float) * ACCUM_STRIDE * (P < 0 ? 0 : (size_t)P), 256); }
 
@@ -398,8 +402,6 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 
 	BRS_CUDA(ensure_slot());
 	BRS_CUDA(cudaMemsetAsync(geom + gl.header, 0, HEADER_BYTES, stream));
-	if (grid_x * grid_y > 0)
-		BRS_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * grid_x * grid_y, stream)); // rasterizer_impl.cu:311
 
 	PreprocessArgs pa{};
 	pa.P = P;
@@ -433,7 +435,7 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
 
 	// R leaves for the host now; the depth sort below does not depend on it.
-	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	BRS_CUDA(cudaEventRecord(t_slot.event, stream));
 
 	char* scratch1 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, depth_scratch_bytes(P)));
@@ -445,7 +447,7 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	          debug, stream);
 
 	BRS_CUDA(cudaEventSynchronize(t_slot.event)); // the one host wait (reference: rasterizer_impl.cu:282)
-	const uint32_t R = *t_slot.pinned;
+	const uint32_t R = t_slot.pinned[0], R1 = t_slot.pinned[1];
 	if (R > (1u << 30))
 		return BRS_ERR_UNSUPPORTED;
 	state->num_rendered = (int)R;
@@ -457,25 +459,35 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	state->binning_bytes = binning_bytes(R);
 	uint32_t* point_list = reinterpret_cast<uint32_t*>(binning);
 
-	if (R > 0) {
-		char* scratch2 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, instance_scratch_bytes(P, R)));
+	if (grid_x * grid_y > 0) {
+		char* scratch2 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, instance_scratch_bytes(P, R1, grid_x, grid_y)));
 		if (scratch2 == nullptr)
 			return BRS_ERR_ALLOC;
-		const size_t rb = align_up(sizeof(uint32_t) * (size_t)R, 256);
-		uint32_t* inst_keys = reinterpret_cast<uint32_t*>(scratch2);
-		uint32_t* inst_ids = reinterpret_cast<uint32_t*>(scratch2 + rb);
+		const size_t rb = align_up(sizeof(uint32_t) * (size_t)R1, 256);
+		uint32_t* cell_keys = reinterpret_cast<uint32_t*>(scratch2);
+		uint32_t* cell_ids = reinterpret_cast<uint32_t*>(scratch2 + rb);
 		uint32_t* sorted_keys = reinterpret_cast<uint32_t*>(scratch2 + 2 * rb);
-		char* sort_scratch = scratch2 + 3 * rb;
-		char* emit_scratch = sort_scratch + sort_scratch_bytes(R);
+		uint32_t* coarse_list = reinterpret_cast<uint32_t*>(scratch2 + 3 * rb);
+		char* sort_scratch = scratch2 + 4 * rb;
+		char* emit_scratch = sort_scratch + sort_scratch_bytes(R1);
+		char* fine_scratch = emit_scratch + emit_scratch_bytes(P);
+		const uint32_t ns_x = supertiles(grid_x), ns = ns_x * supertiles(grid_y);
 
-		BRS_STAGE(BRS_STAGE_EMIT,
-		          launch_emit(order, rect, (size_t)P, grid_x, inst_keys, inst_ids, (size_t)R, emit_scratch, stream), debug,
-		          stream);
-		BRS_STAGE(BRS_STAGE_TILE_SORT,
-		          sort_pairs(inst_keys, inst_ids, sorted_keys, point_list, (size_t)R, 0, tile_bits(grid_x * grid_y),
-		                     sort_scratch, stream),
+		if (R1 > 0) {
+			BRS_STAGE(BRS_STAGE_COARSE_EMIT,
+			          launch_emit(order, rect, (size_t)P, ST_SHIFT, ns_x, cell_keys, cell_ids, (size_t)R1, emit_scratch,
+			                      stream),
+			          debug, stream);
+			BRS_STAGE(BRS_STAGE_COARSE_SORT,
+			          sort_pairs(cell_keys, cell_ids, sorted_keys, coarse_list, (size_t)R1, 0, tile_bits(ns), sort_scratch,
+			                     stream),
+			          debug, stream);
+		}
+		// also writes the (0,0) ranges of empty tiles (reference: cudaMemset, rasterizer_impl.cu:311)
+		BRS_STAGE(BRS_STAGE_FINE_BIN,
+		          launch_fine_binning(sorted_keys, coarse_list, (size_t)R1, rect, grid_x, grid_y, point_list, ranges,
+		                              fine_scratch, stream),
 		          debug, stream);
-		BRS_STAGE(BRS_STAGE_TILE_RANGES, launch_tile_ranges(sorted_keys, (size_t)R, ranges, stream), debug, stream);
 	}
 
 	BlendFwdArgs ba{};

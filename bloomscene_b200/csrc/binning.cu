@@ -1,19 +1,28 @@
-// Binning for sm_100a: depth sort, instance emission, tile sort, tile ranges.
+// Binning for sm_100a: depth sort, two-level tile binning, tile ranges.
 //
 // The reference builds 64-bit keys (tile << 32 | depth bits) for all R (tile, Gaussian) instances
 // and runs one 6-pass CUB radix sort over 12-byte pairs (rasterizer_impl.cu:70-111, 278-318).
 // The same order — ascending (tile, depth bits, Gaussian id), which is what a stable sort of the
-// reference's emission order yields — is produced here with ~4x less memory traffic by splitting it:
+// reference's emission order yields — is produced here without ever sorting R-sized arrays:
 //
 //   1. stable sort of the P Gaussians by depth bits (u32 key, value = id; culled ones carry the
 //      key 0xFFFFFFFF, emit nothing, and may land anywhere)                    -> `order`
-//   2. one fused kernel: exclusive scan of tiles-per-Gaussian in depth order (decoupled look-back,
-//      32 predecessors per poll) + emission of (tile id, Gaussian id) instances
-//   3. stable sort of the instances by tile id only (ceil(log2(#tiles)) bits: 2 passes at 1080p)
-//   4. tile ranges from the sorted tile ids (reference identifyTileRanges, rasterizer_impl.cu:116-138)
+//   2. COARSE level: one fused kernel scans supertiles-per-Gaussian in depth order (decoupled
+//      look-back, 32 predecessors per poll) and emits (supertile id, Gaussian id) instances, a
+//      supertile being 8x8 tiles; R1 ~ 1.3 V of them.  One stable radix pass on the supertile id
+//      (<= 8 bits up to 2048x2048 pixels) turns that into per-supertile lists in depth order.
+//   3. FINE level: every supertile list is cut into slices of 128 entries, one warp per slice.
+//      count  : per slice, how many entries cover each of the supertile's 64 tiles (lane = entry,
+//               one ballot per tile)
+//      scan   : per (supertile, tile) exclusive prefix over the slices; then one exclusive scan over
+//               all tile ids gives every tile's start in `point_list` and the tile `ranges`
+//               (reference identifyTileRanges, rasterizer_impl.cu:116-138: empty tiles stay (0,0))
+//      scatter: the count loop again; the ballot's lower-lane popcount is the stable rank, so ids are
+//               written straight to their final position.
 //
-// Because (1) is stable in id and (3) is stable, instances inside a tile end up ordered by
-// (depth bits, id): exactly the reference's sorted `point_list`.
+// Because (1) is stable in id, (2) is stable, and slices / lanes are walked in list order, instances
+// inside a tile end up ordered by (depth bits, id): exactly the reference's sorted `point_list`.
+// Traffic is ~70 P + 16 R1 + 4 R bytes instead of the reference's 152 R.
 //
 // The radix sort is hand-written.  Each pass over one digit is three kernels:
 //   upsweep   : per 4096-key tile, digit counts (warp match_any + shared atomics)  -> table[digit][tile]
@@ -304,10 +313,19 @@ constexpr int EMIT_THREADS = 256;
 constexpr int EMIT_ITEMS = 4;
 constexpr int EMIT_TILE = EMIT_THREADS * EMIT_ITEMS; // Gaussians per block
 
+// Tile rectangle -> rectangle in cells of (1 << shift) tiles; an empty rectangle stays empty.
+__device__ __forceinline__ uint2 coarsen_rect(uint2 r, uint32_t shift)
+{
+	const uint32_t x0 = r.x & 0xffffu, x1 = r.x >> 16, y0 = r.y & 0xffffu, y1 = r.y >> 16;
+	if (x1 <= x0 || y1 <= y0)
+		return make_uint2(0u, 0u);
+	return make_uint2((x0 >> shift) | ((((x1 - 1) >> shift) + 1) << 16), (y0 >> shift) | ((((y1 - 1) >> shift) + 1) << 16));
+}
+
 __global__ void __launch_bounds__(EMIT_THREADS)
-    emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rect, uint32_t P, uint32_t grid_x,
-                uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ inst_ids, uint32_t R, uint32_t* status,
-                uint32_t* ticket)
+    emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rect, uint32_t P, uint32_t shift,
+                uint32_t grid_x, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ inst_ids, uint32_t R,
+                uint32_t* status, uint32_t* ticket)
 {
 	__shared__ uint32_t s_incl[EMIT_TILE]; // inclusive instance offsets inside this block
 	__shared__ uint32_t s_id[EMIT_TILE];
@@ -331,7 +349,7 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 		uint2 r = make_uint2(0u, 0u);
 		if (s < P) {
 			id = __ldg(order + s);
-			r = __ldg(rect + id);
+			r = coarsen_rect(__ldg(rect + id), shift);
 		}
 		const uint32_t w = (r.x >> 16) - (r.x & 0xffffu);
 		const uint32_t hgt = (r.y >> 16) - (r.y & 0xffffu);
@@ -433,8 +451,8 @@ size_t emit_scratch_bytes(size_t P)
 	return align_up(256 + sizeof(uint32_t) * blocks, 256);
 }
 
-cudaError_t launch_emit(const uint32_t* order, const uint2* rect, size_t P, uint32_t grid_x, uint32_t* tile_keys,
-                        uint32_t* inst_ids, size_t R, void* scratch, cudaStream_t stream)
+cudaError_t launch_emit(const uint32_t* order, const uint2* rect, size_t P, uint32_t shift, uint32_t grid_x,
+                        uint32_t* tile_keys, uint32_t* inst_ids, size_t R, void* scratch, cudaStream_t stream)
 {
 	if (P == 0)
 		return cudaSuccess;
@@ -444,9 +462,298 @@ cudaError_t launch_emit(const uint32_t* order, const uint2* rect, size_t P, uint
 		return e;
 	uint32_t* ticket = static_cast<uint32_t*>(scratch);
 	uint32_t* status = ticket + 64;
-	emit_kernel<<<blocks, EMIT_THREADS, 0, stream>>>(order, rect, (uint32_t)P, grid_x, tile_keys, inst_ids,
+	emit_kernel<<<blocks, EMIT_THREADS, 0, stream>>>(order, rect, (uint32_t)P, shift, grid_x, tile_keys, inst_ids,
 	                                                 (uint32_t)R, status, ticket);
 	count_launch();
+	return cudaGetLastError();
+}
+
+// ---- fine level: supertile lists -> per-tile lists --------------------------------------------------
+
+namespace {
+
+constexpr int FINE_WARPS = 8; // warps (= slices) per CTA of the count / scatter kernels
+
+__device__ __forceinline__ uint32_t spread4(uint32_t b) // bit i of b (i < 4) -> bit 8 i
+{
+	return (b * 0x00204081u) & 0x01010101u;
+}
+
+// Exclusive scan of ceil(n_s / FINE_SLICE) over the supertiles -> slice_base[0..ns]; also copies the
+// list starts.  One CTA (ns is a few hundred).
+__global__ void __launch_bounds__(SORT_THREADS)
+    fine_plan_kernel(const uint2* __restrict__ coarse_ranges, uint32_t ns, uint32_t* __restrict__ slice_base)
+{
+	__shared__ uint32_t s_warp[SORT_WARPS];
+	uint32_t carry = 0;
+	for (uint32_t s0 = 0; s0 < ns; s0 += SORT_THREADS) {
+		const uint32_t s = s0 + threadIdx.x;
+		uint32_t v = 0;
+		if (s < ns) {
+			const uint2 r = coarse_ranges[s];
+			v = (r.y - r.x + FINE_SLICE - 1) / FINE_SLICE;
+		}
+		uint32_t total;
+		const uint32_t ex = block_exclusive_scan_256(v, s_warp, total);
+		if (s < ns)
+			slice_base[s] = carry + ex;
+		carry += total;
+	}
+	if (threadIdx.x == 0)
+		slice_base[ns] = carry;
+}
+
+// One warp per slice of <= FINE_SLICE consecutive entries of one supertile's list (lane = entry, 32
+// at a time, in list order).  For each of the supertile's 64 tiles one ballot says which lanes'
+// rectangles cover it: its popcount is the slice's count for the tile (COUNT pass), its lower-lane
+// popcount the entry's stable rank (SCATTER pass).
+template <bool SCATTER>
+__global__ void __launch_bounds__(FINE_WARPS * 32)
+    fine_kernel(const uint32_t* __restrict__ coarse_list, const uint2* __restrict__ coarse_ranges,
+                const uint32_t* __restrict__ slice_base, const uint2* __restrict__ rect, uint32_t ns, uint32_t ns_x,
+                uint32_t grid_x, uint32_t grid_y, uint32_t* __restrict__ table, const uint32_t* __restrict__ tile_start,
+                uint32_t* __restrict__ point_list)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t sl = blockIdx.x * FINE_WARPS + (threadIdx.x >> 5);
+	if (sl >= __ldg(slice_base + ns))
+		return;
+	// supertile of this slice: last s with slice_base[s] <= sl
+	uint32_t lo_s = 0, hi_s = ns;
+	while (hi_s - lo_s > 1) {
+		const uint32_t mid = (lo_s + hi_s) >> 1;
+		if (__ldg(slice_base + mid) <= sl)
+			lo_s = mid;
+		else
+			hi_s = mid;
+	}
+	const uint32_t st = lo_s;
+	const uint2 cr = __ldg(coarse_ranges + st);
+	const uint32_t begin = cr.x + (sl - __ldg(slice_base + st)) * FINE_SLICE;
+	const uint32_t end = min(begin + (uint32_t)FINE_SLICE, cr.y);
+	const uint32_t tx0 = (st % ns_x) << ST_SHIFT, ty0 = (st / ns_x) << ST_SHIFT;
+
+	// lane l keeps the running value of local tiles l (rows 0..3) and l + 32 (rows 4..7)
+	uint32_t run0 = 0, run1 = 0;
+	if (SCATTER) {
+		const uint32_t x = tx0 + (lane & 7), y = ty0 + (lane >> 3);
+		if (x < grid_x && y < grid_y)
+			run0 = __ldg(tile_start + y * grid_x + x) + table[(size_t)sl * ST_TILES + lane];
+		if (x < grid_x && y + 4 < grid_y)
+			run1 = __ldg(tile_start + (y + 4) * grid_x + x) + table[(size_t)sl * ST_TILES + 32 + lane];
+	}
+
+	for (uint32_t e0 = begin; e0 < end; e0 += 32) {
+		const uint32_t e = e0 + lane;
+		uint32_t id = 0, lo = 0, hi = 0;
+		if (e < end) {
+			id = __ldg(coarse_list + e);
+			const uint2 r = __ldg(rect + id);
+			const int x0 = (int)(r.x & 0xffffu) - (int)tx0, x1 = (int)(r.x >> 16) - (int)tx0;
+			const int y0 = (int)(r.y & 0xffffu) - (int)ty0, y1 = (int)(r.y >> 16) - (int)ty0;
+			const uint32_t cx0 = (uint32_t)max(x0, 0), cx1 = (uint32_t)min(x1, 8);
+			const uint32_t cy0 = (uint32_t)max(y0, 0), cy1 = (uint32_t)min(y1, 8);
+			if (cx1 > cx0 && cy1 > cy0) {
+				const uint32_t cols = ((1u << cx1) - (1u << cx0)) & 0xffu;
+				const uint32_t rows = ((1u << cy1) - (1u << cy0)) & 0xffu;
+				lo = cols * spread4(rows & 15u);
+				hi = cols * spread4(rows >> 4);
+			}
+		}
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			const uint32_t m = half ? hi : lo;
+			if (__ballot_sync(0xffffffffu, m != 0) == 0)
+				continue;
+			uint32_t run = half ? run1 : run0;
+#pragma unroll
+			for (int t = 0; t < 32; t++) {
+				const bool covers = (m >> t) & 1u;
+				const uint32_t b = __ballot_sync(0xffffffffu, covers);
+				if (b == 0)
+					continue;
+				if (SCATTER) {
+					const uint32_t base = __shfl_sync(0xffffffffu, run, t);
+					if (covers)
+						point_list[base + __popc(b & lanemask_lt())] = id;
+				}
+				if (lane == (uint32_t)t)
+					run += __popc(b);
+			}
+			if (half)
+				run1 = run;
+			else
+				run0 = run;
+		}
+	}
+	if (!SCATTER) {
+		table[(size_t)sl * ST_TILES + lane] = run0;
+		table[(size_t)sl * ST_TILES + 32 + lane] = run1;
+	}
+}
+
+// Per supertile (one CTA, 4 groups x 64 tiles): exclusive prefix of the slice counts along the
+// slices, in place, and the per-tile totals into tile_count[tile id].
+__global__ void __launch_bounds__(256)
+    fine_scan_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slice_base, uint32_t ns_x,
+                     uint32_t grid_x, uint32_t grid_y, uint32_t* __restrict__ tile_count)
+{
+	__shared__ uint32_t s_part[4][ST_TILES];
+	const uint32_t st = blockIdx.x;
+	const uint32_t first = __ldg(slice_base + st), nsl = __ldg(slice_base + st + 1) - first;
+	const uint32_t t = threadIdx.x & 63, q = threadIdx.x >> 6;
+	const uint32_t per = (nsl + 3) / 4;
+	const uint32_t j0 = min(q * per, nsl), j1 = min(j0 + per, nsl);
+	uint32_t* col = table + (size_t)first * ST_TILES + t;
+	uint32_t sum = 0;
+#pragma unroll 8
+	for (uint32_t j = j0; j < j1; j++)
+		sum += col[(size_t)j * ST_TILES];
+	s_part[q][t] = sum;
+	__syncthreads();
+	uint32_t run = 0, total = 0;
+#pragma unroll
+	for (uint32_t k = 0; k < 4; k++) {
+		const uint32_t v = s_part[k][t];
+		if (k < q)
+			run += v;
+		total += v;
+	}
+#pragma unroll 8
+	for (uint32_t j = j0; j < j1; j++) {
+		const uint32_t v = col[(size_t)j * ST_TILES];
+		col[(size_t)j * ST_TILES] = run;
+		run += v;
+	}
+	if (q == 0) {
+		const uint32_t x = ((st % ns_x) << ST_SHIFT) + (t & 7), y = ((st / ns_x) << ST_SHIFT) + (t >> 3);
+		if (x < grid_x && y < grid_y)
+			tile_count[y * grid_x + x] = total;
+	}
+}
+
+// Exclusive scan of the per-tile counts in tile-id order -> tile_start, and the tile ranges
+// (reference identifyTileRanges: tiles without instances keep (0, 0)).  One CTA.
+__global__ void __launch_bounds__(1024)
+    tile_offsets_kernel(const uint32_t* __restrict__ tile_count, uint32_t num_tiles, uint32_t* __restrict__ tile_start,
+                        uint2* __restrict__ ranges)
+{
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_carry;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0)
+		s_carry = 0;
+	__syncthreads();
+	for (uint32_t t0 = 0; t0 < num_tiles; t0 += 1024) {
+		const uint32_t t = t0 + threadIdx.x;
+		const uint32_t v = (t < num_tiles) ? tile_count[t] : 0u;
+		uint32_t incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= (uint32_t)o)
+				incl += n;
+		}
+		if (lane == 31)
+			s_warp[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
+				if (lane >= (uint32_t)o)
+					wi += n;
+			}
+			s_warp[lane] = wi - w; // exclusive over warps
+		}
+		__syncthreads();
+		const uint32_t start = s_carry + s_warp[warp] + incl - v;
+		if (t < num_tiles) {
+			tile_start[t] = start;
+			ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
+		}
+		__syncthreads();
+		if (threadIdx.x == 1023)
+			s_carry = start + v;
+		__syncthreads();
+	}
+}
+
+struct FineScratch {
+	uint2* coarse_ranges;  // [ns]
+	uint32_t* slice_base;  // [ns + 1]
+	uint32_t* tile_count;  // [num_tiles]
+	uint32_t* tile_start;  // [num_tiles]
+	uint32_t* table;       // [max_slices][64]
+	size_t total_bytes;
+};
+
+FineScratch carve_fine_scratch(void* scratch, size_t R1, uint32_t grid_x, uint32_t grid_y)
+{
+	FineScratch f{};
+	const size_t ns = (size_t)supertiles(grid_x) * supertiles(grid_y);
+	const size_t num_tiles = (size_t)grid_x * grid_y;
+	const size_t max_slices = R1 / FINE_SLICE + ns;
+	char* p = static_cast<char*>(scratch);
+	size_t off = 0;
+	f.coarse_ranges = reinterpret_cast<uint2*>(p + off);
+	off += align_up(sizeof(uint2) * ns, 256);
+	f.slice_base = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * (ns + 1), 256);
+	f.tile_count = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * num_tiles, 256);
+	f.tile_start = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * num_tiles, 256);
+	f.table = reinterpret_cast<uint32_t*>(p + off);
+	off += align_up(sizeof(uint32_t) * ST_TILES * (max_slices ? max_slices : 1), 256);
+	f.total_bytes = off;
+	return f;
+}
+
+} // namespace
+
+size_t fine_scratch_bytes(size_t R1, uint32_t grid_x, uint32_t grid_y)
+{
+	return carve_fine_scratch(nullptr, R1, grid_x, grid_y).total_bytes;
+}
+
+cudaError_t launch_fine_binning(const uint32_t* sorted_coarse_keys, const uint32_t* coarse_list, size_t R1,
+                                const uint2* rect, uint32_t grid_x, uint32_t grid_y, uint32_t* point_list,
+                                uint2* ranges, void* scratch, cudaStream_t stream)
+{
+	const uint32_t ns_x = supertiles(grid_x), ns = ns_x * supertiles(grid_y);
+	const uint32_t num_tiles = grid_x * grid_y;
+	if (num_tiles == 0)
+		return cudaSuccess;
+	FineScratch f = carve_fine_scratch(scratch, R1, grid_x, grid_y);
+	// coarse_ranges and tile_count start at zero (supertiles / tiles nothing touches are never written)
+	cudaError_t e = cudaMemsetAsync(f.coarse_ranges, 0, (char*)f.tile_start - (char*)f.coarse_ranges, stream);
+	if (e != cudaSuccess)
+		return e;
+	if (R1 > 0) {
+		tile_ranges_kernel<<<(uint32_t)((R1 + 255) / 256), 256, 0, stream>>>(sorted_coarse_keys, (uint32_t)R1,
+		                                                                      f.coarse_ranges);
+		count_launch();
+	}
+	fine_plan_kernel<<<1, SORT_THREADS, 0, stream>>>(f.coarse_ranges, ns, f.slice_base);
+	count_launch();
+	const uint32_t max_slices = (uint32_t)(R1 / FINE_SLICE + ns);
+	const uint32_t blocks = (max_slices + FINE_WARPS - 1) / FINE_WARPS;
+	if (R1 > 0) {
+		fine_kernel<false><<<blocks, FINE_WARPS * 32, 0, stream>>>(coarse_list, f.coarse_ranges, f.slice_base, rect, ns,
+		                                                            ns_x, grid_x, grid_y, f.table, nullptr, nullptr);
+		count_launch();
+		fine_scan_kernel<<<ns, 256, 0, stream>>>(f.table, f.slice_base, ns_x, grid_x, grid_y, f.tile_count);
+		count_launch();
+	}
+	tile_offsets_kernel<<<1, 1024, 0, stream>>>(f.tile_count, num_tiles, f.tile_start, ranges);
+	count_launch();
+	if (R1 > 0) {
+		fine_kernel<true><<<blocks, FINE_WARPS * 32, 0, stream>>>(coarse_list, f.coarse_ranges, f.slice_base, rect, ns,
+		                                                           ns_x, grid_x, grid_y, f.table, f.tile_start, point_list);
+		count_launch();
+	}
 	return cudaGetLastError();
 }
 

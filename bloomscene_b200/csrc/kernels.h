@@ -31,7 +31,7 @@ struct PreprocessArgs {
 	float4* records;      // [3P]
 	uint32_t* depth_key;  // [P]
 	uint2* rect;          // [P]
-	uint32_t* total_tiles; // [1], pre-zeroed
+	uint32_t* total_tiles; // [2], pre-zeroed: R = tile instances, R1 = supertile instances
 };
 cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream);
 
@@ -64,14 +64,22 @@ size_t sort_scratch_bytes(size_t n);
 cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                        size_t n, int begin_bit, int end_bit, void* scratch, cudaStream_t stream);
 
-// Fused exclusive scan of per-Gaussian tile counts (in depth order) + emission of (tile, id)
-// instances.  `order` = Gaussian ids sorted by depth; `rect` packed rectangles.
+// Fused exclusive scan of per-Gaussian cell counts (in depth order) + emission of (cell, id)
+// instances, a cell being (1 << shift)^2 tiles and grid_x the number of cells per row.
+// `order` = Gaussian ids sorted by depth; `rect` packed tile rectangles.
 size_t emit_scratch_bytes(size_t P);
-cudaError_t launch_emit(const uint32_t* order, const uint2* rect, size_t P, uint32_t grid_x, uint32_t* tile_keys,
-                        uint32_t* inst_ids, size_t R, void* scratch, cudaStream_t stream);
+cudaError_t launch_emit(const uint32_t* order, const uint2* rect, size_t P, uint32_t shift, uint32_t grid_x,
+                        uint32_t* cell_keys, uint32_t* inst_ids, size_t n_instances, void* scratch, cudaStream_t stream);
 
-// ranges[tile] = [first, last+1) in the sorted instance list; `ranges` must be pre-zeroed.
-cudaError_t launch_tile_ranges(const uint32_t* sorted_tile_keys, size_t R, uint2* ranges, cudaStream_t stream);
+// ranges[key] = [first, last+1) in a sorted key list; `ranges` must be pre-zeroed.
+cudaError_t launch_tile_ranges(const uint32_t* sorted_keys, size_t n, uint2* ranges, cudaStream_t stream);
+
+// Fine level of the binning: per-supertile lists (sorted_coarse_keys / coarse_list, R1 entries in
+// (supertile, depth, id) order) -> point_list (R ids in (tile, depth, id) order) and tile ranges.
+size_t fine_scratch_bytes(size_t R1, uint32_t grid_x, uint32_t grid_y);
+cudaError_t launch_fine_binning(const uint32_t* sorted_coarse_keys, const uint32_t* coarse_list, size_t R1,
+                                const uint2* rect, uint32_t grid_x, uint32_t grid_y, uint32_t* point_list,
+                                uint2* ranges, void* scratch, cudaStream_t stream);
 
 // ---- blend_fwd.cu -------------------------------------------------------------------------------
 struct BlendFwdArgs {

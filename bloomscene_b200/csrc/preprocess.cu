@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	extern __shared__ float4 s_dyn[]; // SH staging (only when a.shs != nullptr)
 	__shared__ float s_cam[36];
 	__shared__ uint32_t s_vis[PRE_THREADS / 32];
-	__shared__ uint32_t s_tiles[PRE_THREADS / 32];
+	__shared__ uint32_t s_tiles[2][PRE_THREADS / 32];
 
 	stage_camera(s_cam, a.viewmatrix, a.projmatrix, a.campos);
 	__syncthreads();
@@ -199,7 +199,12 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	}
 
 	const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
-	uint32_t tiles = visible ? (g.rect_max.y - g.rect_min.y) * (g.rect_max.x - g.rect_min.x) : 0u;
+	uint32_t tiles = 0u, cells = 0u; // tile / supertile instances of this Gaussian
+	if (visible) {
+		tiles = (g.rect_max.y - g.rect_min.y) * (g.rect_max.x - g.rect_min.x);
+		cells = ((((g.rect_max.x - 1) >> ST_SHIFT) + 1) - (g.rect_min.x >> ST_SHIFT)) *
+		        ((((g.rect_max.y - 1) >> ST_SHIFT) + 1) - (g.rect_min.y >> ST_SHIFT));
+	}
 
 	// ---- colour ----
 	float3 rgb = {0.f, 0.f, 0.f};
@@ -279,20 +284,24 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 		}
 	}
 
-	// ---- grid-wide instance count R (integer -> deterministic) ----
+	// ---- grid-wide instance counts R, R1 (integer -> deterministic) ----
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
+	for (int o = 16; o > 0; o >>= 1) {
 		tiles += __shfl_xor_sync(0xffffffffu, tiles, o);
-	if (lane == 0)
-		s_tiles[warp] = tiles;
+		cells += __shfl_xor_sync(0xffffffffu, cells, o);
+	}
+	if (lane == 0) {
+		s_tiles[0][warp] = tiles;
+		s_tiles[1][warp] = cells;
+	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
+	if (threadIdx.x < 2) {
 		uint32_t sum = 0;
 #pragma unroll
 		for (int w = 0; w < PRE_THREADS / 32; w++)
-			sum += s_tiles[w];
+			sum += s_tiles[threadIdx.x][w];
 		if (sum)
-			atomicAdd(a.total_tiles, sum);
+			atomicAdd(a.total_tiles + threadIdx.x, sum);
 	}
 }
 

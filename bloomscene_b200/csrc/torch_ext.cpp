@@ -380,7 +380,7 @@ pybind11::dict StageTimes()
 	float ms[BRS_NUM_STAGES] = {0};
 	int calls[BRS_NUM_STAGES] = {0};
 	check_status(brs_stage_times(ms, calls), "stage_times");
-	static const char* names[BRS_NUM_STAGES] = {"preprocess", "depth_sort", "emit", "tile_sort", "tile_ranges",
+	static const char* names[BRS_NUM_STAGES] = {"preprocess", "depth_sort", "coarse_emit", "coarse_sort", "fine_bin",
 	                                            "blend_fwd", "blend_bwd", "preprocess_bwd"};
 	pybind11::dict d;
 	for (int i = 0; i < BRS_NUM_STAGES; i++)

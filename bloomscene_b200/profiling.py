@@ -9,6 +9,8 @@ from typing import Dict, Sequence
 
 import torch
 
+from .debug import state_views
+
 
 def profile_views(api, params, cameras: Sequence, bg: torch.Tensor, dL_dcolor: torch.Tensor, rank: int = 0,
                   world: int = 1, max_views: int = 8, warm: int = 1) -> Dict[str, object]:
@@ -20,7 +22,7 @@ def profile_views(api, params, cameras: Sequence, bg: torch.Tensor, dL_dcolor: t
     shs = t.get("shs", e)
     cols = t.get("colors_precomp", e)
     views = list(range(rank, len(cameras), world))[:max_views]
-    agg = {"V": 0, "R": 0, "E": 0, "C": 0, "Eb": 0}
+    agg = {"V": 0, "R": 0, "R1": 0, "E": 0, "C": 0, "Eb": 0}
 
     def one(cam, count: bool):
         R, color, depth, radii, geom, binning, img = _C.rasterize_gaussians(
@@ -34,6 +36,11 @@ def profile_views(api, params, cameras: Sequence, bg: torch.Tensor, dL_dcolor: t
             E, C, Eb = _C.count_pairs(geom, binning, img, params.P, R, cam.image_width, cam.image_height)
             agg["V"] += int((radii > 0).sum().item())
             agg["R"] += R
+            rect = state_views(_C, geom, binning, img, params.P, R, cam.image_width, cam.image_height)["rect"].long()
+            x0, x1, y0, y1 = rect[:, 0] & 0xFFFF, rect[:, 0] >> 16, rect[:, 1] & 0xFFFF, rect[:, 1] >> 16
+            live = (x1 > x0) & (y1 > y0)
+            cells = ((((x1 - 1) >> 3) + 1) - (x0 >> 3)) * ((((y1 - 1) >> 3) + 1) - (y0 >> 3))
+            agg["R1"] += int(cells[live].sum().item())
             agg["E"] += E
             agg["C"] += C
             agg["Eb"] += Eb

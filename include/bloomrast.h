@@ -193,9 +193,9 @@ long long brs_launch_count(int reset);
 enum {
 	BRS_STAGE_PREPROCESS = 0,
 	BRS_STAGE_DEPTH_SORT = 1,
-	BRS_STAGE_EMIT = 2,
-	BRS_STAGE_TILE_SORT = 3,
-	BRS_STAGE_TILE_RANGES = 4,
+	BRS_STAGE_COARSE_EMIT = 2, /* scan + emission of (supertile, Gaussian) instances in depth order */
+	BRS_STAGE_COARSE_SORT = 3, /* stable radix pass(es) on the supertile id */
+	BRS_STAGE_FINE_BIN = 4,    /* per-tile count / scan / scatter -> point_list, tile ranges */
 	BRS_STAGE_BLEND_FWD = 5,
 	BRS_STAGE_BLEND_BWD = 6,
 	BRS_STAGE_PREPROCESS_BWD = 7,

@@ -5,10 +5,18 @@
 //   * the tile starts at max(n_contrib) over its pixels and each warp skips records behind the
 //     max(n_contrib) of ITS 32 pixels (the reference walks them with a per-thread `continue`);
 //   * per-warp conservative culling with the records' alpha>=1/255 boxes (see blend_fwd.cu);
-//   * the nine per-Gaussian partial gradients are reduced across the warp with a transposing
-//     shuffle tree (14 shuffles for 9 values) and leave as ONE predicated RED.ADD.F32 instruction
-//     whose 9 active lanes hit 9 consecutive floats of a 48-byte per-Gaussian accumulator —
-//     instead of 9 separate 32-lane atomics per contributing pair (backward.cu:537,574-583);
+//   * the per-Gaussian gradient sums are NOT reduced pair by pair.  All nine are fixed linear
+//     functions of two per-pixel scalars,
+//         w = G * dL_dalpha            u = alpha * T
+//         dL_dopacity = S(w)           dL_dcolor_c = S(u * dL_dpixel_c)
+//         dL_dmean2D, dL_dconic  <-  S(w dx), S(w dy), S(w dx dx), S(w dx dy), S(w dy dy)
+//     so the pixel loop only stores (w, u) of a contributing record into a warp-private staging
+//     slot (2 STS).  Every 8 staged records the warp "flushes": lane (r, q) takes record r and
+//     pixel row q of the warp's 8x4 block, forms the row's moment / colour sums from 4 LDS.128,
+//     the 4 rows are combined with an 8-shuffle transposing tree, and the record leaves as one
+//     red.global.add.v2.f32 per lane (+1 scalar) on a 48-byte accumulator row.  That is ~20
+//     instructions per contributing (warp, record) instead of ~60 for a 9-value warp reduction,
+//     against the reference's 9 x 32-lane atomics per pair (backward.cu:537,574-583);
 //   * constant factors (0.5*W, 0.5*H, -0.5) are applied once per Gaussian in the preprocess
 //     backward instead of once per pair.
 // Parity quirks kept: the alpha derivative ignores the min(0.99,.) clamp, T is recovered by
@@ -23,39 +31,116 @@ namespace brs {
 namespace {
 
 constexpr int BLEND_THREADS = TILE_X * TILE_Y;
+constexpr int BLEND_WARPS = BLEND_THREADS / 32;
 constexpr int BATCH = 256;
+constexpr int GROUP = 8;         // contributing records staged per warp between flushes (8 records x 4 rows = 32 lanes)
+constexpr int STAGE_STRIDE = 68; // floats per staged record: w[32] | u[32] | 4 pad -> the flush's LDS.128 are conflict-free
 
-// Sum nine per-lane values over the warp.  On return: lanes with (lane & 3) == 0 hold the total of
-// slot (lane >> 2) in `r8`, and every lane holds the total of slot 8 in `r9`.
-__device__ __forceinline__ void warp_reduce9(const float v[9], uint32_t lane, float& r8, float& r9)
+__device__ __forceinline__ float rcp_approx(float x)
 {
-	const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-	float r[4];
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
+{
+	asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// Flush `cnt` (<= GROUP) staged records of this warp.  Lane (r = lane >> 2, q = lane & 3) owns
+// record r and the q-th row (8 pixels) of the warp's pixel block.
+__device__ __forceinline__ void flush_group(const float* __restrict__ stage, const uint32_t* __restrict__ slots, int cnt,
+                                            const float4* __restrict__ s_geo, const float4* __restrict__ s_con,
+                                            const uint32_t* __restrict__ s_id, const float* __restrict__ s_dpx,
+                                            float bxf, float byf, uint32_t lane, float* __restrict__ accum)
+{
+	__syncwarp();
+	const uint32_t r = lane >> 2, q = lane & 3;
+	const bool live = (int)r < cnt;
+	float v[9];
+#pragma unroll
+	for (int i = 0; i < 9; i++)
+		v[i] = 0.f;
+	uint32_t id = 0;
+	if (live) {
+		const uint32_t idx = slots[r];
+		const float4 g = s_geo[idx];
+		const float4 con = s_con[idx];
+		id = s_id[idx];
+		const float4* st = reinterpret_cast<const float4*>(stage + r * STAGE_STRIDE + q * 8);
+		const float4 wa = st[0], wb = st[1], ua = st[8], ub = st[9];
+		const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+		const float u[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+		const float dy = g.y - (byf + (float)q);
+		const float dx0 = g.x - bxf;
+		float S0 = 0.f, Sx = 0.f, Sxx = 0.f;
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			const float dx = dx0 - (float)i;
+			const float t = w[i] * dx;
+			S0 += w[i];
+			Sx += t;
+			Sxx = fmaf(t, dx, Sxx);
+		}
+		const float4* dp = reinterpret_cast<const float4*>(s_dpx + q * 8);
+		float c[3];
+#pragma unroll
+		for (int ch = 0; ch < 3; ch++) {
+			const float4 da = dp[ch * 8], db = dp[ch * 8 + 1];
+			float s = u[0] * da.x;
+			s = fmaf(u[1], da.y, s);
+			s = fmaf(u[2], da.z, s);
+			s = fmaf(u[3], da.w, s);
+			s = fmaf(u[4], db.x, s);
+			s = fmaf(u[5], db.y, s);
+			s = fmaf(u[6], db.z, s);
+			s = fmaf(u[7], db.w, s);
+			c[ch] = s;
+		}
+		const float Sy = dy * S0, Sxy = dy * Sx, Syy = dy * Sy;
+		const float o = con.w;
+		// dL_dG * G = o * w;  dG_ddelx = -G (dx a + dy b),  dG_ddely = -G (dy c + dx b)
+		v[0] = -o * (con.x * Sx + con.y * Sy); // x 0.5*W later
+		v[1] = -o * (con.z * Sy + con.y * Sx); // x 0.5*H later
+		v[2] = o * Sxx;                         // x -0.5 later
+		v[3] = o * Sxy;
+		v[4] = o * Syy;
+		v[5] = S0;
+		v[6] = c[0];
+		v[7] = c[1];
+		v[8] = c[2];
+	}
+	// combine the 4 rows (lanes q = 0..3 of a record): 9 -> 5 -> 3 values per lane, 8 shuffles.
+	// Afterwards lane q holds slots 2q, 2q + 1 in (a, b) and every lane holds slot 8 in c8.
+	const bool h2 = lane & 2, h1 = lane & 1;
+	float r4[4];
 #pragma unroll
 	for (int i = 0; i < 4; i++) {
-		const float send = h16 ? v[i] : v[i + 4];
-		const float keep = h16 ? v[i + 4] : v[i];
-		r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+		const float send = h2 ? v[i] : v[i + 4];
+		const float keep = h2 ? v[i + 4] : v[i];
+		r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
 	}
-	float q[2];
-#pragma unroll
-	for (int i = 0; i < 2; i++) {
-		const float send = h8 ? r[i] : r[i + 2];
-		const float keep = h8 ? r[i + 2] : r[i];
-		q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+	float c8 = v[8] + __shfl_xor_sync(0xffffffffu, v[8], 2);
+	float a, b;
+	{
+		const float send = h1 ? r4[0] : r4[2];
+		const float keep = h1 ? r4[2] : r4[0];
+		a = keep + __shfl_xor_sync(0xffffffffu, send, 1);
 	}
 	{
-		const float send = h4 ? q[0] : q[1];
-		const float keep = h4 ? q[1] : q[0];
-		r8 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+		const float send = h1 ? r4[1] : r4[3];
+		const float keep = h1 ? r4[3] : r4[1];
+		b = keep + __shfl_xor_sync(0xffffffffu, send, 1);
 	}
-	r8 += __shfl_xor_sync(0xffffffffu, r8, 2);
-	r8 += __shfl_xor_sync(0xffffffffu, r8, 1);
-	float w = v[8];
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		w += __shfl_xor_sync(0xffffffffu, w, o);
-	r9 = w;
+	c8 += __shfl_xor_sync(0xffffffffu, c8, 1);
+	if (live) {
+		float* dst = accum + (size_t)id * ACCUM_STRIDE;
+		red_add_v2(dst + 2 * q, a, b);
+		if (q == 0)
+			atomicAdd(dst + 8, c8);
+	}
+	__syncwarp();
 }
 
 __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdArgs a)
@@ -64,7 +149,10 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	__shared__ float4 s_con[BATCH];
 	__shared__ float4 s_col[BATCH];
 	__shared__ uint32_t s_id[BATCH];
-	__shared__ uint32_t s_max[BLEND_THREADS / 32];
+	__shared__ __align__(16) float s_stage[BLEND_WARPS][GROUP * STAGE_STRIDE];
+	__shared__ __align__(16) float s_dpx[BLEND_WARPS][3 * 32];
+	__shared__ uint32_t s_slot[BLEND_WARPS][GROUP];
+	__shared__ uint32_t s_max[BLEND_WARPS];
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -82,6 +170,17 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	float T = T_final;
 	const int last_contributor = inside ? (int)__ldg(a.n_contrib + pix_id) : 0;
 
+	float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f;
+	if (inside) {
+		const size_t plane = (size_t)a.W * a.H;
+		dpx0 = __ldg(a.dL_dpixels + pix_id);
+		dpx1 = __ldg(a.dL_dpixels + plane + pix_id);
+		dpx2 = __ldg(a.dL_dpixels + 2 * plane + pix_id);
+	}
+	s_dpx[warp][lane] = dpx0;
+	s_dpx[warp][32 + lane] = dpx1;
+	s_dpx[warp][64 + lane] = dpx2;
+
 	// records at list positions >= max(n_contrib) are skipped by every pixel of the warp / tile
 	int warp_max = last_contributor;
 #pragma unroll
@@ -92,23 +191,22 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	__syncthreads();
 	int tile_max = 0;
 #pragma unroll
-	for (int w = 0; w < BLEND_THREADS / 32; w++)
+	for (int w = 0; w < BLEND_WARPS; w++)
 		tile_max = max(tile_max, (int)s_max[w]);
 	const int n = min((int)(range.y - range.x), tile_max);
 
 	float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f;
-	float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f;
-	if (inside) {
-		const size_t plane = (size_t)a.W * a.H;
-		dpx0 = __ldg(a.dL_dpixels + pix_id);
-		dpx1 = __ldg(a.dL_dpixels + plane + pix_id);
-		dpx2 = __ldg(a.dL_dpixels + 2 * plane + pix_id);
-	}
 	float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
 	float bg_dot_dpixel = 0.f;
 	bg_dot_dpixel += __ldg(a.bg + 0) * dpx0;
 	bg_dot_dpixel += __ldg(a.bg + 1) * dpx1;
 	bg_dot_dpixel += __ldg(a.bg + 2) * dpx2;
+	const float neg_Tf_bg = -T_final * bg_dot_dpixel;
+
+	float* const stage = s_stage[warp];
+	uint32_t* const slots = s_slot[warp];
+	const float* const dpx_rows = s_dpx[warp];
+	int staged = 0;
 
 	// batches walk the list backwards: shared slot s holds list position n-1-(base+s)
 	for (int base = 0; base < n; base += BATCH) {
@@ -124,12 +222,15 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 		}
 		__syncthreads();
 
+		// slot idx is list position n-1-base-idx; it is in front of this pixel's last contributor
+		// iff idx > first_live (and of this warp's iff idx > warp_first_live)
+		const int first_live = n - 1 - base - last_contributor;
+		const int warp_first_live = n - 1 - base - warp_max;
+
 		for (int c0 = 0; c0 < cnt; c0 += 32) {
-			// first list position of this chunk is the largest; skip whole chunk if behind the warp
 			const int e = c0 + (int)lane;
-			const int pos_e = n - 1 - (base + e);
 			bool hit = false;
-			if (e < cnt && pos_e < warp_max) {
+			if (e < cnt && e > warp_first_live) {
 				const float4 g = s_geo[e];
 				hit = (g.x + g.z >= wx0) && (g.x - g.z <= wx1) && (g.y + g.w >= wy0) && (g.y - g.w <= wy1);
 			}
@@ -138,7 +239,6 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				const int j = __ffs(mask) - 1;
 				mask &= mask - 1;
 				const int idx = c0 + j;
-				const int pos = n - 1 - (base + idx);
 				const float4 g = s_geo[idx];
 				const float4 con = s_con[idx];
 				const float dx = g.x - pixfx;
@@ -149,60 +249,49 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				const float power = __fmaf_rn(s, -0.5f, -t3);
 				const float G = expf(power);
 				const float alpha = fminf(0.99f, __fmul_rn(con.w, G));
-				const bool ok = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+				const bool ok = (idx > first_live) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 				if (!__any_sync(0xffffffffu, ok))
 					continue;
 
 				const float4 col = s_col[idx];
-				float v[9];
-#pragma unroll
-				for (int i = 0; i < 9; i++)
-					v[i] = 0.f;
+				float w_ = 0.f, u_ = 0.f;
 				if (ok) {
 					// 1 - alpha >= 0.01 (alpha is clamped to 0.99): one MUFU.RCP (<= 1 ulp) replaces the
 					// reference's two IEEE divisions; gradients are tolerance-checked (rel-L2 <= 1e-4)
-					const float rcp = __fdividef(1.0f, 1.f - alpha);
+					const float rcp = rcp_approx(1.f - alpha);
 					T = T * rcp;
-					const float dchannel_dcolor = alpha * T;
+					u_ = alpha * T; // dchannel_dcolor
 
-					float dL_dalpha = 0.0f;
-					accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
+					const float om = 1.f - last_alpha;
+					accum_rec0 = last_alpha * last_c0 + om * accum_rec0;
+					accum_rec1 = last_alpha * last_c1 + om * accum_rec1;
+					accum_rec2 = last_alpha * last_c2 + om * accum_rec2;
 					last_c0 = col.x;
-					dL_dalpha += (col.x - accum_rec0) * dpx0;
-					accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
 					last_c1 = col.y;
-					dL_dalpha += (col.y - accum_rec1) * dpx1;
-					accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
 					last_c2 = col.z;
+					float dL_dalpha = (col.x - accum_rec0) * dpx0;
+					dL_dalpha += (col.y - accum_rec1) * dpx1;
 					dL_dalpha += (col.z - accum_rec2) * dpx2;
 					dL_dalpha *= T;
 					last_alpha = alpha;
-					dL_dalpha += (-T_final * rcp) * bg_dot_dpixel;
-
-					const float dL_dG = con.w * dL_dalpha;
-					const float gdx = G * dx;
-					const float gdy = G * dy;
-					const float dG_ddelx = -gdx * con.x - gdy * con.y;
-					const float dG_ddely = -gdy * con.z - gdx * con.y;
-
-					v[0] = dL_dG * dG_ddelx; // x 0.5*W later
-					v[1] = dL_dG * dG_ddely; // x 0.5*H later
-					v[2] = gdx * dx * dL_dG; // x -0.5 later
-					v[3] = gdx * dy * dL_dG;
-					v[4] = gdy * dy * dL_dG;
-					v[5] = G * dL_dalpha;
-					v[6] = dchannel_dcolor * dpx0;
-					v[7] = dchannel_dcolor * dpx1;
-					v[8] = dchannel_dcolor * dpx2;
+					dL_dalpha += neg_Tf_bg * rcp;
+					w_ = G * dL_dalpha;
 				}
-				float r8, r9;
-				warp_reduce9(v, lane, r8, r9);
-				float* dst = a.accum + (size_t)s_id[idx] * ACCUM_STRIDE;
-				if ((lane & 3) == 0)
-					atomicAdd(dst + (lane >> 2), r8);
-				else if (lane == 1)
-					atomicAdd(dst + 8, r9);
+				float* st = stage + staged * STAGE_STRIDE;
+				st[lane] = w_;
+				st[32 + lane] = u_;
+				if (lane == 0)
+					slots[staged] = (uint32_t)idx;
+				if (++staged == GROUP) {
+					flush_group(stage, slots, GROUP, s_geo, s_con, s_id, dpx_rows, wx0, wy0, lane, a.accum);
+					staged = 0;
+				}
 			}
+		}
+		// staged slots refer to this batch's shared records: flush before they are overwritten
+		if (staged) {
+			flush_group(stage, slots, staged, s_geo, s_con, s_id, dpx_rows, wx0, wy0, lane, a.accum);
+			staged = 0;
 		}
 	}
 }

@@ -51,9 +51,9 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 // Flush `cnt` (<= GROUP) staged records of this warp.  Lane (r = lane >> 2, q = lane & 3) owns
 // record r and the q-th row (8 pixels) of the warp's pixel block.
 __device__ __forceinline__ void flush_group(const float* __restrict__ stage, const uint32_t* __restrict__ slots, int cnt,
-                                            const float4* __restrict__ s_geo, const float4* __restrict__ s_con,
-                                            const uint32_t* __restrict__ s_id, const float* __restrict__ s_dpx,
-                                            float bxf, float byf, uint32_t lane, float* __restrict__ accum)
+                                            const StagedRecord* __restrict__ rec, const uint32_t* __restrict__ s_id,
+                                            const float* __restrict__ s_dpx, float bxf, float byf, uint32_t lane,
+                                            float* __restrict__ accum)
 {
 	__syncwarp();
 	const uint32_t r = lane >> 2, q = lane & 3;
@@ -65,8 +65,8 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, con
 	uint32_t id = 0;
 	if (live) {
 		const uint32_t idx = slots[r];
-		const float4 g = s_geo[idx];
-		const float4 con = s_con[idx];
+		const float2 g = *reinterpret_cast<const float2*>(&rec[idx].geo);
+		const float4 con = rec[idx].con;
 		id = s_id[idx];
 		const float4* st = reinterpret_cast<const float4*>(stage + r * STAGE_STRIDE + q * 8);
 		const float4 wa = st[0], wb = st[1], ua = st[8], ub = st[9];
@@ -145,10 +145,8 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, con
 
 __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdArgs a)
 {
-	__shared__ float4 s_geo[BATCH];
-	__shared__ float4 s_con[BATCH];
-	__shared__ float4 s_col[BATCH];
-	__shared__ uint32_t s_id[BATCH];
+	__shared__ StagedRecord s_rec[2][BATCH];
+	__shared__ uint32_t s_ids[2][BATCH];
 	__shared__ __align__(16) float s_stage[BLEND_WARPS][GROUP * STAGE_STRIDE];
 	__shared__ __align__(16) float s_dpx[BLEND_WARPS][3 * 32];
 	__shared__ uint32_t s_slot[BLEND_WARPS][GROUP];
@@ -208,19 +206,27 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	const float* const dpx_rows = s_dpx[warp];
 	int staged = 0;
 
-	// batches walk the list backwards: shared slot s holds list position n-1-(base+s)
-	for (int base = 0; base < n; base += BATCH) {
-		__syncthreads();
-		const int cnt = min(BATCH, n - base);
-		if ((int)tid < cnt) {
-			const uint32_t id = __ldg(a.point_list + range.x + (n - 1 - (base + (int)tid)));
-			const float4* rec = a.records + 3 * (size_t)id;
-			s_id[tid] = id;
-			s_geo[tid] = __ldg(rec);
-			s_con[tid] = __ldg(rec + 1);
-			s_col[tid] = __ldg(rec + 2);
+	// batches walk the list backwards: slot s of the batch at `base` holds list position n-1-(base+s).
+	// Double-buffered cp.async staging as in the forward: batch b+1 lands while batch b is processed.
+	const uint32_t* list_end = a.point_list + range.x + (n - 1);
+	if ((int)tid < n) {
+		const uint32_t id = __ldg(list_end - tid);
+		s_ids[0][tid] = id;
+		stage_record_async(&s_rec[0][tid], a.records, id);
+	}
+	uint32_t id_next = (BATCH + (int)tid < n) ? __ldg(list_end - (BATCH + tid)) : 0u;
+
+	for (int base = 0, buf = 0; base < n; base += BATCH, buf ^= 1) {
+		cp_async_wait_all();
+		__syncthreads(); // buffer `buf` complete and visible; buffer `buf ^ 1` no longer read
+		if (base + BATCH + (int)tid < n) {
+			s_ids[buf ^ 1][tid] = id_next;
+			stage_record_async(&s_rec[buf ^ 1][tid], a.records, id_next);
 		}
-		__syncthreads();
+		id_next = (base + 2 * BATCH + (int)tid < n) ? __ldg(list_end - (base + 2 * BATCH + tid)) : 0u;
+		const StagedRecord* rec = s_rec[buf];
+		const uint32_t* s_id = s_ids[buf];
+		const int cnt = min(BATCH, n - base);
 
 		// slot idx is list position n-1-base-idx; it is in front of this pixel's last contributor
 		// iff idx > first_live (and of this warp's iff idx > warp_first_live)
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 			const int e = c0 + (int)lane;
 			bool hit = false;
 			if (e < cnt && e > warp_first_live) {
-				const float4 g = s_geo[e];
+				const float4 g = rec[e].geo;
 				hit = (g.x + g.z >= wx0) && (g.x - g.z <= wx1) && (g.y + g.w >= wy0) && (g.y - g.w <= wy1);
 			}
 			uint32_t mask = __ballot_sync(0xffffffffu, hit);
@@ -239,8 +245,9 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				const int j = __ffs(mask) - 1;
 				mask &= mask - 1;
 				const int idx = c0 + j;
-				const float4 g = s_geo[idx];
-				const float4 con = s_con[idx];
+				const StagedRecord* r = rec + idx;
+				const float2 g = *reinterpret_cast<const float2*>(&r->geo);
+				const float4 con = r->con;
 				const float dx = g.x - pixfx;
 				const float dy = g.y - pixfy;
 				const float t1 = __fmul_rn(dy, __fmul_rn(dy, con.z));
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				if (!__any_sync(0xffffffffu, ok))
 					continue;
 
-				const float4 col = s_col[idx];
+				const float4 col = r->col;
 				float w_ = 0.f, u_ = 0.f;
 				if (ok) {
 					// 1 - alpha >= 0.01 (alpha is clamped to 0.99): one MUFU.RCP (<= 1 ulp) replaces the
@@ -283,14 +290,14 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				if (lane == 0)
 					slots[staged] = (uint32_t)idx;
 				if (++staged == GROUP) {
-					flush_group(stage, slots, GROUP, s_geo, s_con, s_id, dpx_rows, wx0, wy0, lane, a.accum);
+					flush_group(stage, slots, GROUP, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 					staged = 0;
 				}
 			}
 		}
 		// staged slots refer to this batch's shared records: flush before they are overwritten
 		if (staged) {
-			flush_group(stage, slots, staged, s_geo, s_con, s_id, dpx_rows, wx0, wy0, lane, a.accum);
+			flush_group(stage, slots, staged, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 			staged = 0;
 		}
 	}

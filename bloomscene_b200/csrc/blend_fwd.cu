@@ -2,7 +2,9 @@
 //
 // One CTA per 16x16 tile (tile ids are parity outputs), 8 warps, each warp owns a compact 8x4-pixel
 // block of the tile.  A batch of up to 256 sorted Gaussian records is staged into shared memory by
-// the CTA (three 128-bit gathers per record); then every warp
+// the CTA with three 16-byte cp.async gathers per record into a DOUBLE buffer: batch b+1 lands
+// while batch b is blended, the ids of batch b+2 are already in a register, and one barrier per
+// batch both publishes the new buffer and retires the old one.  Then every warp
 //   1. culls the batch against ITS pixel block: lane k tests record k's conservative alpha>=1/255
 //      bounding box (hx,hy from preprocess) -> ballot -> bit mask of records that can touch the warp;
 //   2. walks only the set bits, evaluating all 32 pixels for that record with warp-uniform smem
@@ -27,9 +29,7 @@ constexpr int BATCH = 256;
 
 __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdArgs a)
 {
-	__shared__ float4 s_geo[BATCH]; // x, y, hx, hy
-	__shared__ float4 s_con[BATCH]; // conic a, b, c, opacity
-	__shared__ float4 s_col[BATCH]; // r, g, b, depth
+	__shared__ StagedRecord s_rec[2][BATCH]; // geo {x, y, hx, hy} | con {a, b, c, opacity} | col {r, g, b, depth}
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -43,43 +43,46 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 
 	const uint2 range = __ldg(a.ranges + tile_y * a.grid_x + tile_x);
 	const int n = (int)(range.y - range.x);
+	const uint32_t* list = a.point_list + range.x;
 
 	bool done = !inside;
 	float T = 1.0f;
 	uint32_t last_contributor = 0;
 	float C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, acc = 0.000001f;
 
-	for (int base = 0; base < n; base += BATCH) {
+	// prologue: batch 0 in flight, ids of batch 1 in a register
+	if ((int)tid < n)
+		stage_record_async(&s_rec[0][tid], a.records, __ldg(list + tid));
+	uint32_t id_next = (BATCH + (int)tid < n) ? __ldg(list + BATCH + tid) : 0u;
+
+	for (int base = 0, buf = 0; base < n; base += BATCH, buf ^= 1) {
+		cp_async_wait_all();
 		bool warp_done = __all_sync(0xffffffffu, done);
+		// one barrier per batch: buffer `buf` is complete and visible, buffer `buf ^ 1` is no longer read
 		if (__syncthreads_and(warp_done))
 			break;
+		if (base + BATCH + (int)tid < n)
+			stage_record_async(&s_rec[buf ^ 1][tid], a.records, id_next);
+		id_next = (base + 2 * BATCH + (int)tid < n) ? __ldg(list + base + 2 * BATCH + tid) : 0u;
 
+		const StagedRecord* rec = s_rec[buf];
 		const int cnt = min(BATCH, n - base);
-		if ((int)tid < cnt) {
-			const uint32_t id = __ldg(a.point_list + range.x + base + tid);
-			const float4* rec = a.records + 3 * (size_t)id;
-			s_geo[tid] = __ldg(rec);
-			s_con[tid] = __ldg(rec + 1);
-			s_col[tid] = __ldg(rec + 2);
-		}
-		__syncthreads();
-
 		for (int c0 = 0; c0 < cnt && !warp_done; c0 += 32) {
 			const int e = c0 + (int)lane;
 			bool hit = false;
 			if (e < cnt) {
-				const float4 g = s_geo[e];
+				const float4 g = rec[e].geo;
 				hit = (g.x + g.z >= wx0) && (g.x - g.z <= wx1) && (g.y + g.w >= wy0) && (g.y - g.w <= wy1);
 			}
 			uint32_t mask = __ballot_sync(0xffffffffu, hit);
 			while (mask) {
 				const int j = __ffs(mask) - 1;
 				mask &= mask - 1;
-				const int idx = c0 + j;
-				const float4 g = s_geo[idx];
-				const float4 con = s_con[idx];
-				const float dx = g.x - pixfx;
-				const float dy = g.y - pixfy;
+				const StagedRecord* r = rec + (c0 + j);
+				const float2 gxy = *reinterpret_cast<const float2*>(&r->geo);
+				const float4 con = r->con;
+				const float dx = gxy.x - pixfx;
+				const float dy = gxy.y - pixfy;
 				const float t1 = __fmul_rn(dy, __fmul_rn(dy, con.z));
 				const float s = __fmaf_rn(dx, __fmul_rn(dx, con.x), t1);
 				const float t3 = __fmul_rn(dy, __fmul_rn(dx, con.y));
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 					ok = false;
 				}
 				if (__any_sync(0xffffffffu, ok)) {
-					const float4 col = s_col[idx];
+					const float4 col = r->col;
 					if (ok) {
 						C0 = __fmaf_rn(T, __fmul_rn(alpha, col.x), C0);
 						C1 = __fmaf_rn(T, __fmul_rn(alpha, col.y), C1);
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 						D = __fmaf_rn(T, __fmul_rn(alpha, col.w), D);
 						acc = __fmaf_rn(T, alpha, acc);
 						T = test_T;
-						last_contributor = (uint32_t)(base + idx + 1);
+						last_contributor = (uint32_t)(base + c0 + j + 1);
 					}
 				} else if (__all_sync(0xffffffffu, done)) {
 					warp_done = true;
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 			}
 		}
 	}
+	cp_async_wait_all();
 
 	if (inside) {
 		const size_t plane = (size_t)a.W * a.H;

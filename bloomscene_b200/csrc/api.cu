@@ -254,7 +254,8 @@ size_t brs_binning_bytes(int R) { return binning_bytes(R < 0 ? 0 : (size_t)R); }
 size_t brs_image_bytes(int W, int H) { return image_layout(W, H).total; }
 size_t brs_sort_scratch_bytes(int n) { return sort_scratch_bytes(n < 0 ? 0 : (size_t)n); }
 
-static size_t depth_scratch_bytes(size_t P) { return align_up(sizeof(uint32_t) * P, 256) + sort_scratch_bytes(P); }
+// sorted keys (final) + first-pass keys/values + the sort's own scratch (tables + ping-pong pair)
+static size_t depth_scratch_bytes(size_t P) { return 3 * align_up(sizeof(uint32_t) * P, 256) + sort_scratch_bytes(P); }
 // R1 = supertile instances (what the coarse level sorts); never more than the tile instances R.
 static size_t instance_scratch_bytes(size_t P, size_t R1, uint32_t grid_x, uint32_t grid_y)
 {
@@ -434,23 +435,60 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	pa.total_tiles = d_total;
 	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
 
-	// R leaves for the host now; the depth sort below does not depend on it.
-	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	// R, R1 and the depth-key range leave for the host now.  The first radix pass of the depth sort (low
+	// 8 key bits) needs none of them and keeps the GPU busy during the host round trip.
+	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	BRS_CUDA(cudaEventRecord(t_slot.event, stream));
 
 	char* scratch1 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, depth_scratch_bytes(P)));
 	if (scratch1 == nullptr)
 		return BRS_ERR_ALLOC;
+	const size_t pb = align_up(sizeof(uint32_t) * (size_t)P, 256);
 	uint32_t* sorted_depth = reinterpret_cast<uint32_t*>(scratch1);
-	BRS_STAGE(BRS_STAGE_DEPTH_SORT, sort_pairs(depth_key, nullptr, sorted_depth, order, (size_t)P, 0, 32,
-	                     scratch1 + align_up(sizeof(uint32_t) * (size_t)P, 256), stream),
-	          debug, stream);
+	uint32_t* first_keys = reinterpret_cast<uint32_t*>(scratch1 + pb);
+	uint32_t* first_vals = reinterpret_cast<uint32_t*>(scratch1 + 2 * pb);
+	char* depth_sort_scratch = scratch1 + 3 * pb;
+	BRS_STAGE(BRS_STAGE_DEPTH_SORT,
+	          sort_pass(depth_key, nullptr, first_keys, first_vals, (size_t)P, 0u, 0, 8, depth_sort_scratch, stream), debug,
+	          stream);
 
 	BRS_CUDA(cudaEventSynchronize(t_slot.event)); // the one host wait (reference: rasterizer_impl.cu:282)
 	const uint32_t R = t_slot.pinned[0], R1 = t_slot.pinned[1];
+	const uint32_t key_min = ~t_slot.pinned[2], key_max = t_slot.pinned[3];
 	if (R > (1u << 30))
 		return BRS_ERR_UNSUPPORTED;
 	state->num_rendered = (int)R;
+
+	// Remaining passes of the depth sort.  Visible keys lie in [key_min, key_max]; subtracting a bias
+	// that is a multiple of 256 keeps the first pass's digit, preserves order and ties, and leaves only
+	// bit_length(key_max - bias) significant bits (23-24 for a scene a few units deep instead of 32).
+	// Culled Gaussians (key 0xFFFFFFFF) wrap to arbitrary places in `order`; they emit nothing.
+	{
+		const uint32_t bias = key_min <= key_max ? (key_min & ~0xFFu) : 0u;
+		const uint32_t span = key_min <= key_max ? key_max - bias : 0u;
+		int nbits = 8;
+		while (nbits < 32 && (span >> nbits) != 0u)
+			nbits++;
+		const int rest = nbits > 8 ? nbits - 8 : 1;
+		const int passes = (rest + 7) / 8;
+		const int base_bits = rest / passes, extra = rest % passes;
+		uint32_t *tmp_keys = nullptr, *tmp_vals = nullptr;
+		sort_tmp_buffers(depth_sort_scratch, (size_t)P, &tmp_keys, &tmp_vals);
+		const uint32_t* kin = first_keys;
+		const uint32_t* vin = first_vals;
+		int shift = 8;
+		for (int p = 0; p < passes; p++) {
+			const int bits = base_bits + (p < extra ? 1 : 0);
+			const bool to_out = ((passes - 1 - p) & 1) == 0;
+			uint32_t* ko = to_out ? sorted_depth : tmp_keys;
+			uint32_t* vo = to_out ? order : tmp_vals;
+			BRS_STAGE(BRS_STAGE_DEPTH_SORT, sort_pass(kin, vin, ko, vo, (size_t)P, bias, shift, bits, depth_sort_scratch, stream),
+			          debug, stream);
+			kin = ko;
+			vin = vo;
+			shift += bits;
+		}
+	}
 
 	char* binning = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_BINNING, binning_bytes(R)));
 	if (binning == nullptr)

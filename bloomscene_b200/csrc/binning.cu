@@ -12,13 +12,13 @@
 //      supertile being 8x8 tiles; R1 ~ 1.3 V of them.  One stable radix pass on the supertile id
 //      (<= 8 bits up to 2048x2048 pixels) turns that into per-supertile lists in depth order.
 //   3. FINE level: every supertile list is cut into slices of 128 entries, one warp per slice.
-//      count  : per slice, how many entries cover each of the supertile's 64 tiles (lane = entry,
-//               one ballot per tile)
+//      count  : per slice, how many entries cover each of the supertile's 64 tiles (lane = tile owner,
+//               entries broadcast one by one in list order)
 //      scan   : per (supertile, tile) exclusive prefix over the slices; then one exclusive scan over
 //               all tile ids gives every tile's start in `point_list` and the tile `ranges`
 //               (reference identifyTileRanges, rasterizer_impl.cu:116-138: empty tiles stay (0,0))
-//      scatter: the count loop again; the ballot's lower-lane popcount is the stable rank, so ids are
-//               written straight to their final position.
+//      scatter: the count loop again; every tile owner appends the ids covering its tile at its running
+//               position, so ids are written straight to their final place in stable order.
 //
 // Because (1) is stable in id, (2) is stable, and slices / lanes are walked in list order, instances
 // inside a tile end up ordered by (depth bits, id): exactly the reference's sorted `point_list`.
@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 
 // ---- upsweep: digit counts of one tile ------------------------------------------------------------
 __global__ void __launch_bounds__(SORT_THREADS)
-    upsweep_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, int bits, uint32_t tiles,
+    upsweep_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t bias, int shift, int bits, uint32_t tiles,
                    uint32_t* __restrict__ table)
 {
 	__shared__ uint32_t s_cnt[RADIX_MAX];
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
 		const bool valid = (tid + i * SORT_THREADS) < valid_count;
-		const uint32_t d = (key[i] >> shift) & mask;
+		const uint32_t d = ((key[i] - bias) >> shift) & mask;
 		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
 		if (valid && (uint32_t)(__ffs(peers) - 1) == lane)
 			atomicAdd(s_cnt + d, (uint32_t)__popc(peers));
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(SORT_THREADS) scan_kernel(uint32_t* __restrict
 // ---- downsweep: stable scatter of one tile --------------------------------------------------------
 __global__ void __launch_bounds__(SORT_THREADS)
     downsweep_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint32_t* __restrict__ kout,
-                     uint32_t* __restrict__ vout, uint32_t n, int shift, int bits, uint32_t tiles,
+                     uint32_t* __restrict__ vout, uint32_t n, uint32_t bias, int shift, int bits, uint32_t tiles,
                      const uint32_t* __restrict__ table, const uint32_t* __restrict__ totals)
 {
 	__shared__ uint32_t s_cnt[SORT_WARPS][RADIX_MAX];
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
 		const bool valid = (wbase + i * 32) < valid_count;
-		const uint32_t d = (key[i] >> shift) & mask;
+		const uint32_t d = ((key[i] - bias) >> shift) & mask;
 		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
 		const int leader = __ffs(peers) - 1;
 		uint32_t old = 0;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 	for (int i = 0; i < SORT_ITEMS; i++) {
 		const uint32_t li = wbase + i * 32;
 		if (li < valid_count) {
-			const uint32_t d = (key[i] >> shift) & mask;
+			const uint32_t d = ((key[i] - bias) >> shift) & mask;
 			const uint32_t pos = s_digit_start[d] + s_cnt[warp][d] + rank[i];
 			s_keys[pos] = key[i];
 			s_vals[pos] = vin ? __ldg(vin + base + li) : base + li;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 		const uint32_t j = tid + i * SORT_THREADS;
 		if (j < valid_count) {
 			const uint32_t k = s_keys[j];
-			const uint32_t g = s_goff[(k >> shift) & mask] + j;
+			const uint32_t g = s_goff[((k - bias) >> shift) & mask] + j;
 			kout[g] = k;
 			vout[g] = s_vals[j];
 		}
@@ -271,6 +271,30 @@ SortScratch carve_sort_scratch(void* scratch, size_t n)
 
 size_t sort_scratch_bytes(size_t n) { return carve_sort_scratch(nullptr, n).total_bytes; }
 
+void sort_tmp_buffers(void* scratch, size_t n, uint32_t** tmp_keys, uint32_t** tmp_vals)
+{
+	SortScratch s = carve_sort_scratch(scratch, n);
+	*tmp_keys = s.tmp_keys;
+	*tmp_vals = s.tmp_vals;
+}
+
+cudaError_t sort_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout, size_t n, uint32_t bias,
+                      int shift, int bits, void* scratch, cudaStream_t stream)
+{
+	if (n == 0)
+		return cudaSuccess;
+	SortScratch s = carve_sort_scratch(scratch, n);
+	const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+	upsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, (uint32_t)n, bias, shift, bits, tiles, s.table);
+	scan_kernel<<<1u << bits, SORT_THREADS, 0, stream>>>(s.table, tiles, s.totals);
+	downsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, (uint32_t)n, bias, shift, bits, tiles,
+	                                                     s.table, s.totals);
+	count_launch();
+	count_launch();
+	count_launch();
+	return cudaGetLastError();
+}
+
 cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                        size_t n, int begin_bit, int end_bit, void* scratch, cudaStream_t stream)
 {
@@ -282,7 +306,6 @@ cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_
 	const int passes = (nbits + 7) / 8;
 	const int base_bits = nbits / passes, extra = nbits % passes;
 	SortScratch s = carve_sort_scratch(scratch, n);
-	const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
 	const uint32_t* kin = keys_in;
 	const uint32_t* vin = vals_in;
 	int shift = begin_bit;
@@ -291,13 +314,9 @@ cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_
 		const bool to_out = ((passes - 1 - p) & 1) == 0;
 		uint32_t* ko = to_out ? keys_out : s.tmp_keys;
 		uint32_t* vo = to_out ? vals_out : s.tmp_vals;
-		upsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, (uint32_t)n, shift, bits, tiles, s.table);
-		scan_kernel<<<1u << bits, SORT_THREADS, 0, stream>>>(s.table, tiles, s.totals);
-		downsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, ko, vo, (uint32_t)n, shift, bits, tiles, s.table,
-		                                                     s.totals);
-		count_launch();
-		count_launch();
-		count_launch();
+		cudaError_t e = sort_pass(kin, vin, ko, vo, n, 0u, shift, bits, scratch, stream);
+		if (e != cudaSuccess)
+			return e;
 		kin = ko;
 		vin = vo;
 		shift += bits;
@@ -503,10 +522,12 @@ __global__ void __launch_bounds__(SORT_THREADS)
 		slice_base[ns] = carry;
 }
 
-// One warp per slice of <= FINE_SLICE consecutive entries of one supertile's list (lane = entry, 32
-// at a time, in list order).  For each of the supertile's 64 tiles one ballot says which lanes'
-// rectangles cover it: its popcount is the slice's count for the tile (COUNT pass), its lower-lane
-// popcount the entry's stable rank (SCATTER pass).
+// One warp per slice of <= FINE_SLICE consecutive entries of one supertile's list.  Entries are read 32
+// at a time (lane = entry, list order): each lane builds the 64-bit mask of the supertile's tiles its
+// rectangle covers.  Then the roles flip: lane t OWNS local tiles t (rows 0..3) and t + 32 (rows 4..7)
+// and the warp walks the 32 entries in list order, broadcasting one entry's mask (and id) per step.
+// The owner of a covered tile bumps its private running position (COUNT pass) and writes the id there
+// (SCATTER pass) - no ballots, no ranks: walking entries in order IS the stable order.
 template <bool SCATTER>
 __global__ void __launch_bounds__(FINE_WARPS * 32)
     fine_kernel(const uint32_t* __restrict__ coarse_list, const uint2* __restrict__ coarse_ranges,
@@ -560,30 +581,26 @@ __global__ void __launch_bounds__(FINE_WARPS * 32)
 				hi = cols * spread4(rows >> 4);
 			}
 		}
-#pragma unroll
-		for (int half = 0; half < 2; half++) {
-			const uint32_t m = half ? hi : lo;
-			if (__ballot_sync(0xffffffffu, m != 0) == 0)
-				continue;
-			uint32_t run = half ? run1 : run0;
-#pragma unroll
-			for (int t = 0; t < 32; t++) {
-				const bool covers = (m >> t) & 1u;
-				const uint32_t b = __ballot_sync(0xffffffffu, covers);
-				if (b == 0)
-					continue;
-				if (SCATTER) {
-					const uint32_t base = __shfl_sync(0xffffffffu, run, t);
-					if (covers)
-						point_list[base + __popc(b & lanemask_lt())] = id;
-				}
-				if (lane == (uint32_t)t)
-					run += __popc(b);
+		const uint32_t cnt = min(32u, end - e0);
+		if (SCATTER) {
+#pragma unroll 8
+			for (uint32_t j = 0; j < cnt; j++) {
+				const uint32_t mlo = __shfl_sync(0xffffffffu, lo, j);
+				const uint32_t mhi = __shfl_sync(0xffffffffu, hi, j);
+				const uint32_t idj = __shfl_sync(0xffffffffu, id, j);
+				if ((mlo >> lane) & 1u)
+					point_list[run0++] = idj;
+				if ((mhi >> lane) & 1u)
+					point_list[run1++] = idj;
 			}
-			if (half)
-				run1 = run;
-			else
-				run0 = run;
+		} else {
+#pragma unroll 8
+			for (uint32_t j = 0; j < cnt; j++) {
+				const uint32_t mlo = __shfl_sync(0xffffffffu, lo, j);
+				const uint32_t mhi = __shfl_sync(0xffffffffu, hi, j);
+				run0 += (mlo >> lane) & 1u;
+				run1 += (mhi >> lane) & 1u;
+			}
 		}
 	}
 	if (!SCATTER) {

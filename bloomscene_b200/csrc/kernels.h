@@ -31,7 +31,7 @@ struct PreprocessArgs {
 	float4* records;      // [3P]
 	uint32_t* depth_key;  // [P]
 	uint2* rect;          // [P]
-	uint32_t* total_tiles; // [2], pre-zeroed: R = tile instances, R1 = supertile instances
+	uint32_t* total_tiles; // [4], pre-zeroed: R = tile instances, R1 = supertile instances, max(~depth bits), max(depth bits) over visible
 };
 cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream);
 
@@ -63,6 +63,11 @@ size_t sort_scratch_bytes(size_t n);
 // keys_out/vals_out; keys_in/vals_in are not modified.  tmp buffers for ping-pong live in scratch.
 cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                        size_t n, int begin_bit, int end_bit, void* scratch, cudaStream_t stream);
+// One stable pass on the digit ((key - bias) >> shift) & ((1 << bits) - 1), bits <= 8; in != out.
+cudaError_t sort_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
+                      uint32_t bias, int shift, int bits, void* scratch, cudaStream_t stream);
+// The ping-pong buffers inside a sort scratch area (n keys + n values).
+void sort_tmp_buffers(void* scratch, size_t n, uint32_t** tmp_keys, uint32_t** tmp_vals);
 
 // Fused exclusive scan of per-Gaussian cell counts (in depth order) + emission of (cell, id)
 // instances, a cell being (1 << shift)^2 tiles and grid_x the number of cells per row.

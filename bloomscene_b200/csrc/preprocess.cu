@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	extern __shared__ float4 s_dyn[]; // SH staging (only when a.shs != nullptr)
 	__shared__ float s_cam[36];
 	__shared__ uint32_t s_vis[PRE_THREADS / 32];
-	__shared__ uint32_t s_tiles[2][PRE_THREADS / 32];
+	__shared__ uint32_t s_tiles[4][PRE_THREADS / 32];
 
 	stage_camera(s_cam, a.viewmatrix, a.projmatrix, a.campos);
 	__syncthreads();
@@ -284,15 +284,22 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 		}
 	}
 
-	// ---- grid-wide instance counts R, R1 (integer -> deterministic) ----
+	// ---- grid-wide instance counts R, R1 and the range of the visible depth keys (integers ->
+	// deterministic).  The range lets the depth sort skip the key bits all visible Gaussians share.
+	uint32_t inv_min = visible ? ~__float_as_uint(g.depth) : 0u; // max of ~key == ~min key
+	uint32_t key_max = visible ? __float_as_uint(g.depth) : 0u;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
 		tiles += __shfl_xor_sync(0xffffffffu, tiles, o);
 		cells += __shfl_xor_sync(0xffffffffu, cells, o);
+		inv_min = max(inv_min, __shfl_xor_sync(0xffffffffu, inv_min, o));
+		key_max = max(key_max, __shfl_xor_sync(0xffffffffu, key_max, o));
 	}
 	if (lane == 0) {
 		s_tiles[0][warp] = tiles;
 		s_tiles[1][warp] = cells;
+		s_tiles[2][warp] = inv_min;
+		s_tiles[3][warp] = key_max;
 	}
 	__syncthreads();
 	if (threadIdx.x < 2) {
@@ -302,6 +309,13 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 			sum += s_tiles[threadIdx.x][w];
 		if (sum)
 			atomicAdd(a.total_tiles + threadIdx.x, sum);
+	} else if (threadIdx.x < 4) {
+		uint32_t m = 0;
+#pragma unroll
+		for (int w = 0; w < PRE_THREADS / 32; w++)
+			m = max(m, s_tiles[threadIdx.x][w]);
+		if (m)
+			atomicMax(a.total_tiles + threadIdx.x, m);
 	}
 }
 

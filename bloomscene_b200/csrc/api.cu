@@ -563,9 +563,13 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 		return BRS_OK;
 	const int W = view->image_width, H = view->image_height;
 	const int M = g->shs ? view->sh_coeffs : 0;
-	if (radii == nullptr || grads->dL_dmeans2D == nullptr || grads->dL_dcolors == nullptr ||
-	    grads->dL_dopacity == nullptr || grads->dL_dmeans3D == nullptr || grads->dL_dcov3D == nullptr ||
-	    grads->dL_dscales == nullptr || grads->dL_drotations == nullptr || (M > 0 && grads->dL_dsh == nullptr))
+	const bool acc = grads->accumulate != 0;
+	const bool has_sr = g->scales != nullptr;
+	// plain mode needs every tensor; accumulate mode only those of the inputs that were given
+	if (radii == nullptr || grads->dL_dmeans2D == nullptr || grads->dL_dopacity == nullptr ||
+	    grads->dL_dmeans3D == nullptr || (M > 0 && grads->dL_dsh == nullptr) ||
+	    ((!acc || M == 0) && grads->dL_dcolors == nullptr) || ((!acc || !has_sr) && grads->dL_dcov3D == nullptr) ||
+	    ((!acc || has_sr) && (grads->dL_dscales == nullptr || grads->dL_drotations == nullptr)))
 		return BRS_ERR_INVALID_ARG;
 	const GeomLayout gl = geom_layout(P);
 	const ImageLayout il = image_layout(W, H);
@@ -624,6 +628,7 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 	pb.focal_y = H / (2.0f * view->tanfovy);
 	pb.focal_x = W / (2.0f * view->tanfovx);
 	pb.accum = accum;
+	pb.accumulate = acc ? 1 : 0;
 	pb.dL_dmeans2D = grads->dL_dmeans2D;
 	pb.dL_dcolors = grads->dL_dcolors;
 	pb.dL_dopacity = grads->dL_dopacity;

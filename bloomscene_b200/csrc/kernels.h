@@ -132,7 +132,8 @@ struct PreprocessBwdArgs {
 	int W, H;
 	float tan_fovx, tan_fovy, focal_x, focal_y;
 	const float* accum; // [P][12] from the blend backward
-	// outputs, every element written
+	int accumulate;     // 0: every output element is written; 1: see brs_grads.accumulate
+	// outputs
 	float* dL_dmeans2D;   // [P,3]
 	float* dL_dcolors;    // [P,3]
 	float* dL_dopacity;   // [P]

@@ -8,6 +8,10 @@
 //   * writes EVERY element of every gradient tensor (zeros for Gaussians with radii <= 0), so the
 //     caller needs no zero-fill: the reference zero-fills (108 + 12 M) bytes per Gaussian first
 //     (rasterize_points.cu:154-162);
+//   * or, in ACCUMULATE mode (brs_grads.accumulate, used by the view-sharded step), adds the parameter
+//     gradients of the visible Gaussians straight into the caller's gradient bucket, which replaces
+//     one fresh (44 + 12 M)-byte-per-Gaussian tensor set plus a read-modify-write pass over the
+//     bucket per view by a single read-modify-write of the visible rows;
 //   * recomputes cov3D and the SH colour sign (`clamped`) with the forward's device functions
 //     instead of reading stored copies;
 //   * stages SH rows (in) and dL_dsh rows (out) through shared memory so that global traffic is
@@ -386,24 +390,52 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(Preproc
 			cov3d_backward(scale, a.scale_modifier, rot, o_cov, o_scale, o_rot);
 	}
 
-	// ---- per-Gaussian outputs (every row written) ----
+	// ---- per-Gaussian outputs ----
+	// plain mode: every row of every tensor is written (zeros for culled Gaussians);
+	// accumulate mode: parameter gradients of VISIBLE Gaussians are added to what the buffers hold,
+	// other rows are left alone; dL_dmeans2D is a per-view statistic and is always overwritten.
 	if (in_range) {
 		float* p;
 		p = a.dL_dmeans2D + 3 * (size_t)idx;
 		p[0] = o_mean2D.x; p[1] = o_mean2D.y; p[2] = 0.f;
-		p = a.dL_dcolors + 3 * (size_t)idx;
-		p[0] = o_color.x; p[1] = o_color.y; p[2] = o_color.z;
-		a.dL_dopacity[idx] = o_opacity;
-		p = a.dL_dmeans3D + 3 * (size_t)idx;
-		p[0] = o_mean3D.x; p[1] = o_mean3D.y; p[2] = o_mean3D.z;
-		p = a.dL_dcov3D + 6 * (size_t)idx;
+		if (!a.accumulate) {
+			p = a.dL_dcolors + 3 * (size_t)idx;
+			p[0] = o_color.x; p[1] = o_color.y; p[2] = o_color.z;
+			a.dL_dopacity[idx] = o_opacity;
+			p = a.dL_dmeans3D + 3 * (size_t)idx;
+			p[0] = o_mean3D.x; p[1] = o_mean3D.y; p[2] = o_mean3D.z;
+			p = a.dL_dcov3D + 6 * (size_t)idx;
 #pragma unroll
-		for (int i = 0; i < 6; i++)
-			p[i] = o_cov[i];
-		p = a.dL_dscales + 3 * (size_t)idx;
-		p[0] = o_scale.x; p[1] = o_scale.y; p[2] = o_scale.z;
-		p = a.dL_drotations + 4 * (size_t)idx;
-		p[0] = o_rot.x; p[1] = o_rot.y; p[2] = o_rot.z; p[3] = o_rot.w;
+			for (int i = 0; i < 6; i++)
+				p[i] = o_cov[i];
+			p = a.dL_dscales + 3 * (size_t)idx;
+			p[0] = o_scale.x; p[1] = o_scale.y; p[2] = o_scale.z;
+			p = a.dL_drotations + 4 * (size_t)idx;
+			p[0] = o_rot.x; p[1] = o_rot.y; p[2] = o_rot.z; p[3] = o_rot.w;
+		} else if (visible) {
+			float* pm = a.dL_dmeans3D + 3 * (size_t)idx;
+			float* po = a.dL_dopacity + idx;
+			const float m0 = pm[0], m1 = pm[1], m2 = pm[2], op = po[0];
+			if (a.scales != nullptr) {
+				float* ps = a.dL_dscales + 3 * (size_t)idx;
+				float* pr = a.dL_drotations + 4 * (size_t)idx;
+				const float s0 = ps[0], s1 = ps[1], s2 = ps[2];
+				const float r0 = pr[0], r1 = pr[1], r2 = pr[2], r3 = pr[3];
+				ps[0] = s0 + o_scale.x; ps[1] = s1 + o_scale.y; ps[2] = s2 + o_scale.z;
+				pr[0] = r0 + o_rot.x; pr[1] = r1 + o_rot.y; pr[2] = r2 + o_rot.z; pr[3] = r3 + o_rot.w;
+			} else {
+				p = a.dL_dcov3D + 6 * (size_t)idx;
+#pragma unroll
+				for (int i = 0; i < 6; i++)
+					p[i] += o_cov[i];
+			}
+			if (a.shs == nullptr) {
+				p = a.dL_dcolors + 3 * (size_t)idx;
+				p[0] += o_color.x; p[1] += o_color.y; p[2] += o_color.z;
+			}
+			pm[0] = m0 + o_mean3D.x; pm[1] = m1 + o_mean3D.y; pm[2] = m2 + o_mean3D.z;
+			po[0] = op + o_opacity;
+		}
 	}
 
 	// ---- dL_dsh rows: dL_dsh[k] = fact[k] * dL_dRGB, written coalesced through shared memory ----
@@ -421,11 +453,23 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(Preproc
 		const int rows = min(PB_THREADS, a.P - block_first);
 		if (VEC) {
 			float4* dst = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)block_first * 12;
+			float4 old[12];
+			if (a.accumulate) {
+				// all loads first (memory-level parallelism), rows of culled Gaussians are skipped
+#pragma unroll
+				for (int k = 0; k < 12; k++) {
+					const int f = threadIdx.x + PB_THREADS * k;
+					const int row = f / 12;
+					old[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+					if (row < rows && ((s_vis[row >> 5] >> (row & 31)) & 1u))
+						old[k] = dst[f];
+				}
+			}
 #pragma unroll
 			for (int k = 0; k < 12; k++) {
 				const int f = threadIdx.x + PB_THREADS * k;
 				const int row = f / 12, col = f - row * 12;
-				if (row < rows) {
+				if (row < rows && (!a.accumulate || ((s_vis[row >> 5] >> (row & 31)) & 1u))) {
 					const float* fr = s_fact + row * FACT_PITCH;
 					float o[4];
 #pragma unroll
@@ -433,7 +477,10 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(Preproc
 						const int e = col * 4 + q;
 						o[q] = fr[e / 3] * fr[16 + (e % 3)];
 					}
-					dst[f] = make_float4(o[0], o[1], o[2], o[3]);
+					if (a.accumulate)
+						dst[f] = make_float4(old[k].x + o[0], old[k].y + o[1], old[k].z + o[2], old[k].w + o[3]);
+					else
+						dst[f] = make_float4(o[0], o[1], o[2], o[3]);
 				}
 			}
 		} else {
@@ -442,7 +489,11 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(Preproc
 			for (int f = threadIdx.x; f < total; f += PB_THREADS) {
 				const int row = f / row_f, e = f - row * row_f;
 				const float* fr = s_fact + row * FACT_PITCH;
-				dst[f] = fr[e / 3] * fr[16 + (e % 3)];
+				const float val = fr[e / 3] * fr[16 + (e % 3)];
+				if (!a.accumulate)
+					dst[f] = val;
+				else if ((s_vis[row >> 5] >> (row & 31)) & 1u)
+					dst[f] += val;
 			}
 		}
 	}

@@ -145,6 +145,89 @@ RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& mea
 	return std::make_tuple(state.num_rendered, out_color, out_depth, radii, ctx.geom, ctx.binning, ctx.image);
 }
 
+namespace {
+
+// Shared body of the two backward bindings: tensors -> C structs -> brs_backward with `grads`.
+void run_backward(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                  const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+                  const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                  const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                  const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth, const torch::Tensor& sh,
+                  const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+                  const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug, const int M,
+                  const brs_grads& grads, const char* what)
+{
+	const int P = means3D.size(0);
+	const int H = dL_dout_color.size(1);
+	const int W = dL_dout_color.size(2);
+	AllocCtx ctx;
+	ctx.byte_opts = torch::TensorOptions(torch::kByte).device(means3D.device());
+
+	torch::Tensor k[13];
+	brs_view view{};
+	view.image_width = W;
+	view.image_height = H;
+	view.tanfovx = tan_fovx;
+	view.tanfovy = tan_fovy;
+	view.scale_modifier = scale_modifier;
+	view.sh_degree = degree;
+	view.sh_coeffs = M;
+	view.prefiltered = 0;
+	view.debug = debug;
+	view.bg = req_ptr(background, k[0], "bg");
+	view.viewmatrix = req_ptr(viewmatrix, k[1], "viewmatrix");
+	view.projmatrix = req_ptr(projmatrix, k[2], "projmatrix");
+	view.campos = opt_ptr(campos, k[3], "campos");
+
+	brs_gaussians g{};
+	g.P = P;
+	g.means3D = req_ptr(means3D, k[4], "means3D");
+	g.opacities = g.means3D; // not read by backward (opacity lives in the forward records); non-NULL for validation
+	g.shs = opt_ptr(sh, k[6], "shs");
+	g.colors_precomp = opt_ptr(colors, k[7], "colors_precomp");
+	g.scales = opt_ptr(scales, k[8], "scales");
+	g.rotations = opt_ptr(rotations, k[9], "rotations");
+	g.cov3D_precomp = opt_ptr(cov3D_precomp, k[10], "cov3D_precomp");
+
+	TORCH_CHECK(radii.is_cuda() && radii.scalar_type() == torch::kInt32, "radii must be a CUDA int32 tensor");
+	torch::Tensor radii_c = radii.contiguous();
+	const float* dcol = req_ptr(dL_dout_color, k[11], "dL_dout_color");
+	const float* ddepth = opt_ptr(dL_dout_depth, k[12], "dL_dout_depth");
+
+	torch::Tensor geom_c = geomBuffer.contiguous(), bin_c = binningBuffer.contiguous(), img_c = imageBuffer.contiguous();
+	brs_fwd_state state{};
+	state.geom = geom_c.data_ptr();
+	state.geom_bytes = (size_t)geom_c.numel();
+	state.binning = bin_c.numel() ? bin_c.data_ptr() : nullptr;
+	state.binning_bytes = (size_t)bin_c.numel();
+	state.image = img_c.data_ptr();
+	state.image_bytes = (size_t)img_c.numel();
+	state.num_rendered = R;
+
+	int st = brs_backward(&view, &g, radii_c.data_ptr<int>(), &state, dcol, ddepth, &grads, alloc_cb, &ctx,
+	                      current_stream());
+	check_status(st, what);
+}
+
+int sh_coeffs_of(const torch::Tensor& sh)
+{
+	return (sh.numel() != 0 && sh.size(0) != 0) ? (int)sh.size(1) : 0;
+}
+
+// Gradient sink of the accumulate binding: absent (undefined / empty) -> NULL, else a contiguous CUDA
+// float32 tensor of exactly `numel` elements that is updated in place.
+float* sink_ptr(const c10::optional<torch::Tensor>& t, int64_t numel, const char* name)
+{
+	if (!t.has_value() || !t->defined() || t->numel() == 0)
+		return nullptr;
+	TORCH_CHECK(t->is_cuda() && t->scalar_type() == torch::kFloat32 && t->is_contiguous(), name,
+	            " sink must be a contiguous CUDA float32 tensor");
+	TORCH_CHECK(t->numel() == numel, name, " sink has the wrong number of elements");
+	return t->data_ptr<float>();
+}
+
+} // namespace
+
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
            torch::Tensor>
 RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D,
@@ -160,13 +243,7 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
 	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
 	c10::cuda::CUDAGuard guard(means3D.device());
 	const int P = means3D.size(0);
-	const int H = dL_dout_color.size(1);
-	const int W = dL_dout_color.size(2);
-
-	int M = 0;
-	if (sh.numel() != 0 && sh.size(0) != 0) {
-		M = sh.size(1);
-	}
+	const int M = sh_coeffs_of(sh);
 
 	auto opts = means3D.options().dtype(torch::kFloat32);
 	torch::Tensor dL_dmeans3D = torch::empty({P, 3}, opts);
@@ -179,51 +256,6 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
 	torch::Tensor dL_drotations = torch::empty({P, 4}, opts);
 
 	if (P != 0) {
-		AllocCtx ctx;
-		ctx.byte_opts = torch::TensorOptions(torch::kByte).device(means3D.device());
-
-		torch::Tensor k[13];
-		brs_view view{};
-		view.image_width = W;
-		view.image_height = H;
-		view.tanfovx = tan_fovx;
-		view.tanfovy = tan_fovy;
-		view.scale_modifier = scale_modifier;
-		view.sh_degree = degree;
-		view.sh_coeffs = M;
-		view.prefiltered = 0;
-		view.debug = debug;
-		view.bg = req_ptr(background, k[0], "bg");
-		view.viewmatrix = req_ptr(viewmatrix, k[1], "viewmatrix");
-		view.projmatrix = req_ptr(projmatrix, k[2], "projmatrix");
-		view.campos = opt_ptr(campos, k[3], "campos");
-
-		brs_gaussians g{};
-		g.P = P;
-		g.means3D = req_ptr(means3D, k[4], "means3D");
-		g.opacities = g.means3D; // not read by backward (opacity lives in the forward records); non-NULL for validation
-		g.shs = opt_ptr(sh, k[6], "shs");
-		g.colors_precomp = opt_ptr(colors, k[7], "colors_precomp");
-		g.scales = opt_ptr(scales, k[8], "scales");
-		g.rotations = opt_ptr(rotations, k[9], "rotations");
-		g.cov3D_precomp = opt_ptr(cov3D_precomp, k[10], "cov3D_precomp");
-
-		TORCH_CHECK(radii.is_cuda() && radii.scalar_type() == torch::kInt32, "radii must be a CUDA int32 tensor");
-		torch::Tensor radii_c = radii.contiguous();
-		const float* dcol = req_ptr(dL_dout_color, k[11], "dL_dout_color");
-		const float* ddepth = opt_ptr(dL_dout_depth, k[12], "dL_dout_depth");
-
-		torch::Tensor geom_c = geomBuffer.contiguous(), bin_c = binningBuffer.contiguous(),
-		              img_c = imageBuffer.contiguous();
-		brs_fwd_state state{};
-		state.geom = geom_c.data_ptr();
-		state.geom_bytes = (size_t)geom_c.numel();
-		state.binning = bin_c.numel() ? bin_c.data_ptr() : nullptr;
-		state.binning_bytes = (size_t)bin_c.numel();
-		state.image = img_c.data_ptr();
-		state.image_bytes = (size_t)img_c.numel();
-		state.num_rendered = R;
-
 		brs_grads grads{};
 		grads.dL_dmeans2D = dL_dmeans2D.data_ptr<float>();
 		grads.dL_dcolors = dL_dcolors.data_ptr<float>();
@@ -233,14 +265,53 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
 		grads.dL_dsh = M > 0 ? dL_dsh.data_ptr<float>() : nullptr;
 		grads.dL_dscales = dL_dscales.data_ptr<float>();
 		grads.dL_drotations = dL_drotations.data_ptr<float>();
-
-		int st = brs_backward(&view, &g, radii_c.data_ptr<int>(), &state, dcol, ddepth, &grads, alloc_cb, &ctx,
-		                      current_stream());
-		check_status(st, "rasterize_gaussians_backward");
+		grads.accumulate = 0;
+		run_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+		             projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth, sh, degree, campos, geomBuffer, R,
+		             binningBuffer, imageBuffer, debug, M, grads, "rasterize_gaussians_backward");
 	}
 
 	return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
 	                       dL_drotations);
+}
+
+// Extension (no reference counterpart): the same backward, but the parameter gradients are ADDED in
+// place to caller-owned sinks (brs_grads.accumulate) instead of being returned as fresh tensors; only
+// the per-view dL_dmeans2D is returned.  Used by the view-sharded step, whose sinks are slices of
+// the flat allreduce bucket.
+torch::Tensor RasterizeGaussiansBackwardAccumulateCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
+    const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+    const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+    const float tan_fovx, const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& sh, const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug,
+    const c10::optional<torch::Tensor>& sink_means3D, const c10::optional<torch::Tensor>& sink_colors,
+    const c10::optional<torch::Tensor>& sink_opacity, const c10::optional<torch::Tensor>& sink_cov3D,
+    const c10::optional<torch::Tensor>& sink_sh, const c10::optional<torch::Tensor>& sink_scales,
+    const c10::optional<torch::Tensor>& sink_rotations)
+{
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
+	c10::cuda::CUDAGuard guard(means3D.device());
+	const int64_t P = means3D.size(0);
+	const int M = sh_coeffs_of(sh);
+	torch::Tensor dL_dmeans2D = torch::empty({P, 3}, means3D.options().dtype(torch::kFloat32));
+	if (P != 0) {
+		brs_grads grads{};
+		grads.dL_dmeans2D = dL_dmeans2D.data_ptr<float>();
+		grads.dL_dmeans3D = sink_ptr(sink_means3D, P * 3, "means3D");
+		grads.dL_dopacity = sink_ptr(sink_opacity, P, "opacity");
+		grads.dL_dcolors = sink_ptr(sink_colors, P * 3, "colors_precomp");
+		grads.dL_dcov3D = sink_ptr(sink_cov3D, P * 6, "cov3D_precomp");
+		grads.dL_dsh = sink_ptr(sink_sh, P * M * 3, "shs");
+		grads.dL_dscales = sink_ptr(sink_scales, P * 3, "scales");
+		grads.dL_drotations = sink_ptr(sink_rotations, P * 4, "rotations");
+		grads.accumulate = 1;
+		run_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+		             projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth, sh, degree, campos, geomBuffer, R,
+		             binningBuffer, imageBuffer, debug, M, grads, "rasterize_gaussians_backward_accumulate");
+	}
+	return dL_dmeans2D;
 }
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix)
@@ -396,6 +467,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("probe_fp32_tflops", []() { return brs_probe_fp32_tflops(current_stream()); });
 	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
 	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+	m.def("rasterize_gaussians_backward_accumulate", &RasterizeGaussiansBackwardAccumulateCUDA);
 	m.def("rasterize_aussians_filter", &RasterizeGaussiansfilterCUDA);
 	m.def("mark_visible", &markVisible);
 	m.def("sort_pairs", &SortPairs, pybind11::arg("keys"), pybind11::arg("vals") = pybind11::none(),

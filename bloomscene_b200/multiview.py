@@ -81,10 +81,13 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
     mine = shard_views(len(cameras), rank, world)
     loss_sum = torch.zeros((), dtype=torch.float32, device=params.flat.device)
     visible = []
+    # the native rasterizer adds parameter gradients straight into the bucket slices (grad_sink);
+    # any other rasterizer (the reference build, the CPU stand-in of the tests) goes through autograd
+    sink = params.grads() if getattr(rasterizer_cls, "supports_grad_sink", False) else None
     for vi in mine:
         cam = cameras[vi]
         settings = raster_settings(cam, params.sh_degree, bg, GaussianRasterizationSettings)
-        rast = rasterizer_cls(raster_settings=settings)
+        rast = rasterizer_cls(settings, grad_sink=sink) if sink is not None else rasterizer_cls(raster_settings=settings)
         means2D = torch.zeros_like(params.tensors["means3D"], requires_grad=True)
         color, radii, depth = rast(means3D=params.tensors["means3D"], means2D=means2D,
                                    opacities=params.tensors["opacities"], shs=params.get("shs"),

@@ -67,7 +67,7 @@ def bind(_C) -> SimpleNamespace:
 
         @staticmethod
         def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                    raster_settings):
+                    raster_settings, grad_sink=None):
             rs = raster_settings
             out = _guarded(
                 _C.rasterize_gaussians,
@@ -78,6 +78,7 @@ def bind(_C) -> SimpleNamespace:
                 "\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
             num_rendered, color, depth, radii, geom, binning, image = out
             ctx.raster_settings = rs
+            ctx.grad_sink = grad_sink
             ctx.num_rendered = num_rendered
             ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom,
                                   binning, image)
@@ -87,6 +88,17 @@ def bind(_C) -> SimpleNamespace:
         def backward(ctx, grad_out_color, grad_radii, grad_depth):
             rs = ctx.raster_settings
             colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, image = ctx.saved_tensors
+            if ctx.grad_sink is not None:
+                # extension: parameter gradients are added in place to the caller's sinks by the kernel
+                # (brs_grads.accumulate); autograd only carries the per-view means2D gradient
+                k = ctx.grad_sink
+                d_means2D = _C.rasterize_gaussians_backward_accumulate(
+                    rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                    rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, sh, rs.sh_degree,
+                    rs.campos, geom, ctx.num_rendered, binning, image, rs.debug,
+                    k.get("means3D"), k.get("colors_precomp"), k.get("opacities"), k.get("cov3D_precomp"), k.get("shs"),
+                    k.get("scales"), k.get("rotations"))
+                return None, d_means2D, None, None, None, None, None, None, None, None
             g = _guarded(
                 _C.rasterize_gaussians_backward,
                 (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
@@ -97,20 +109,39 @@ def bind(_C) -> SimpleNamespace:
             d_means2D, d_colors, d_opacities, d_means3D, d_cov3D, d_sh, d_scales, d_rotations = g
             # one gradient per autograd input, in input order (reference __init__.py:144-154);
             # grad_radii carries nothing and grad_depth is plumbed down but unused by the kernels
-            return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None
+            return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None
+
+    has_sink = hasattr(_C, "rasterize_gaussians_backward_accumulate")
 
     def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                            raster_settings):
-        # reference __init__.py:21-42
+                            raster_settings, grad_sink=None):
+        # reference __init__.py:21-42; `grad_sink` is an extension (see GaussianRasterizer)
+        if grad_sink is not None:
+            if not has_sink:
+                raise Exception('this native module has no in-place gradient accumulation (grad_sink)')
+            given = {"means3D": means3D, "opacities": opacities, "shs": sh, "colors_precomp": colors_precomp,
+                     "scales": scales, "rotations": rotations, "cov3D_precomp": cov3Ds_precomp}
+            for name, t in given.items():
+                if t.numel() != 0 and t.requires_grad and name not in grad_sink:
+                    raise Exception(f'grad_sink has no entry for {name}, whose gradient would be dropped')
         return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                         cov3Ds_precomp, raster_settings)
+                                         cov3Ds_precomp, raster_settings, grad_sink)
 
     class GaussianRasterizer(nn.Module):
-        """reference __init__.py:172-249: forward / visible_filter / markVisible with the same signatures."""
+        """reference __init__.py:172-249: forward / visible_filter / markVisible with the same signatures.
 
-        def __init__(self, raster_settings):
+        Extension: `grad_sink` (default None = reference behaviour) maps input names ("means3D", "opacities",
+        "shs" | "colors_precomp", "scales", "rotations" | "cov3D_precomp") to contiguous fp32 tensors of the
+        inputs' shapes.  With it, backward ADDS those inputs' gradients to the sinks inside the kernel and
+        autograd receives None for them — a multi-view step accumulates straight into its allreduce bucket
+        instead of materialising (44 + 12 M) bytes per Gaussian per view and adding them afterwards."""
+
+        supports_grad_sink = has_sink
+
+        def __init__(self, raster_settings, grad_sink=None):
             super().__init__()
             self.raster_settings = raster_settings
+            self.grad_sink = grad_sink
 
         def markVisible(self, positions):
             rs = self.raster_settings
@@ -127,7 +158,7 @@ def bind(_C) -> SimpleNamespace:
                 raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
             opt = lambda t: _absent() if t is None else t
             return rasterize_gaussians(means3D, means2D, opt(shs), opt(colors_precomp), opacities, opt(scales),
-                                       opt(rotations), opt(cov3D_precomp), self.raster_settings)
+                                       opt(rotations), opt(cov3D_precomp), self.raster_settings, self.grad_sink)
 
         def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
             rs = self.raster_settings

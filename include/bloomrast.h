@@ -110,6 +110,13 @@ typedef struct brs_grads {
 	float* dL_dsh;        /* [P,M,3] or NULL when M == 0 */
 	float* dL_dscales;    /* [P,3]          */
 	float* dL_drotations; /* [P,4]          */
+	/* 0 (reference behaviour): every element of every tensor above is written, zeros for culled
+	 * Gaussians (the reference zero-fills first: rasterize_points.cu:154-162).
+	 * 1 (extension for multi-view steps): the gradients of the inputs that were given — means3D,
+	 * opacity, sh | colors_precomp, scales + rotations | cov3D_precomp — are ADDED to what the
+	 * buffers hold, for visible Gaussians only; tensors of absent inputs may be NULL and are not
+	 * touched; dL_dmeans2D (a per-view statistic) is still overwritten. */
+	int accumulate;
 } brs_grads;
 
 /* --- entry points ------------------------------------------------------------------------- */

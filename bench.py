@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--views", type=int, default=N_VIEWS)
     ap.add_argument("--cpu-views", type=int, default=3, help="views of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a rank are dealt onto (ours only)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "cpu" else a.warmup
 
@@ -161,7 +162,7 @@ def main():
                           + (" + NCCL allreduce of the 236 MB gradient bucket" if world > 1 else ""),
               "P": cfg["P"], "views": a.views, "resolution": [W, H], "sh_degree": 3,
               "l2": "inputs larger than L2 (236 MB of parameters re-read per view, ~0.5 GB working set vs 126 MB L2)",
-              "parallelism": f"view-sharded dp{world}"}
+              "parallelism": f"view-sharded dp{world}", "streams_per_rank": a.streams if a.impl == "ours" else 1}
 
     # ---- CPU port as its own arm -------------------------------------------------------------------
     if a.impl == "cpu":
@@ -231,7 +232,8 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        return view_sharded_step(params, cams, bg, api.GaussianRasterizer, loss_fn, rank=rank_eff, world=world_eff)
+        return view_sharded_step(params, cams, bg, api.GaussianRasterizer, loss_fn, rank=rank_eff, world=world_eff,
+                                 streams=a.streams)
 
     def step_e2e():
         with torch.no_grad():

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	const float pixfx = (float)px, pixfy = (float)py;
 	const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
 
+	const ExpConsts ek = {a.exp_c_scale, a.exp_c_252};
 	const uint2 range = __ldg(a.ranges + tile_y * a.grid_x + tile_x);
 
 	const float T_final = inside ? __ldg(a.final_T + pix_id) : 0.0f;
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				const float s = __fmaf_rn(dx, __fmul_rn(dx, con.x), t1);
 				const float t3 = __fmul_rn(dy, __fmul_rn(dx, con.y));
 				const float power = __fmaf_rn(s, -0.5f, -t3);
-				const float G = expf(power);
+				const float G = expf_exact(power, ek);
 				const float alpha = fminf(0.99f, __fmul_rn(con.w, G));
 				const bool ok = (idx > first_live) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 				if (!__any_sync(0xffffffffu, ok))
@@ -305,8 +306,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 
 } // namespace
 
-cudaError_t launch_blend_backward(const BlendBwdArgs& a, cudaStream_t stream)
+cudaError_t launch_blend_backward(const BlendBwdArgs& args, cudaStream_t stream)
 {
+	BlendBwdArgs a = args;
+	const ExpConsts ek = exp_consts();
+	a.exp_c_scale = ek.c_scale;
+	a.exp_c_252 = ek.c_252;
 	if (a.W <= 0 || a.H <= 0)
 		return cudaSuccess;
 	dim3 grid(a.grid_x, a.grid_y, 1);

@@ -15,7 +15,7 @@
 //
 // Arithmetic is pinned to the reference's sm_100a SASS (nvcc default -fmad=true) with explicit
 // intrinsics, because alpha decides threshold tests (1/255, T<1e-4) that flip whole contributions:
-//   power = fma(fma(dx, dx*a, dy*(dy*c)), -0.5, -(dy*(dx*b)));  alpha = min(0.99, o*expf(power));
+//   power = fma(fma(dx, dx*a, dy*(dy*c)), -0.5, -(dy*(dx*b)));  alpha = min(0.99, o*expf_exact(power, ek));
 //   C = fma(T, alpha*col, C);  D = fma(T, alpha*depth, D);  acc = fma(T, alpha, acc).
 #include "common.cuh"
 #include "kernels.h"
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 	const float pixfx = (float)px, pixfy = (float)py;
 	const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
 
+	const ExpConsts ek = {a.exp_c_scale, a.exp_c_252};
 	const uint2 range = __ldg(a.ranges + tile_y * a.grid_x + tile_x);
 	const int n = (int)(range.y - range.x);
 	const uint32_t* list = a.point_list + range.x;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 				const float s = __fmaf_rn(dx, __fmul_rn(dx, con.x), t1);
 				const float t3 = __fmul_rn(dy, __fmul_rn(dx, con.y));
 				const float power = __fmaf_rn(s, -0.5f, -t3);
-				const float alpha = fminf(0.99f, __fmul_rn(con.w, expf(power)));
+				const float alpha = fminf(0.99f, __fmul_rn(con.w, expf_exact(power, ek)));
 				bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 				const float test_T = __fmul_rn(T, 1.0f - alpha);
 				if (ok && test_T < 0.0001f) {
@@ -127,8 +128,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 
 } // namespace
 
-cudaError_t launch_blend_forward(const BlendFwdArgs& a, cudaStream_t stream)
+cudaError_t launch_blend_forward(const BlendFwdArgs& args, cudaStream_t stream)
 {
+	BlendFwdArgs a = args;
+	const ExpConsts ek = exp_consts();
+	a.exp_c_scale = ek.c_scale;
+	a.exp_c_252 = ek.c_252;
 	if (a.W <= 0 || a.H <= 0)
 		return cudaSuccess;
 	dim3 grid(a.grid_x, a.grid_y, 1);

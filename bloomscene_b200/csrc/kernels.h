@@ -88,6 +88,7 @@ cudaError_t launch_fine_binning(const uint32_t* sorted_coarse_keys, const uint32
 
 // ---- blend_fwd.cu -------------------------------------------------------------------------------
 struct BlendFwdArgs {
+	float exp_c_scale, exp_c_252; // constants of expf_exact (common.cuh), filled by the launcher
 	const uint2* ranges;
 	const uint32_t* point_list;
 	const float4* records;
@@ -103,6 +104,7 @@ cudaError_t launch_blend_forward(const BlendFwdArgs& a, cudaStream_t stream);
 
 // ---- blend_bwd.cu -------------------------------------------------------------------------------
 struct BlendBwdArgs {
+	float exp_c_scale, exp_c_252; // constants of expf_exact (common.cuh), filled by the launcher
 	const uint2* ranges;
 	const uint32_t* point_list;
 	const float4* records;

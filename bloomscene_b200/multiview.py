@@ -39,6 +39,7 @@ class GaussianParams:
         self.flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         self.grad_bucket = torch.zeros_like(self.flat)
         self.tensors: Dict[str, torch.Tensor] = {}
+        self._lanes: List = []
         off = 0
         for n, sz in zip(self.names, sizes):
             seg = self.flat[off:off + sz].view(tensors[n].shape)
@@ -54,6 +55,25 @@ class GaussianParams:
 
     def zero_grad(self):
         self.grad_bucket.zero_()
+        for b, _ in self._lanes:
+            b.zero_()
+
+    def lane_sinks(self, n: int) -> List[Dict[str, torch.Tensor]]:
+        """`n` gradient sinks with the layout of `grads()`: the bucket itself plus n-1 private buckets, one
+        per concurrent stream of the step (two kernels adding into one bucket at the same time would race)."""
+        while len(self._lanes) < n - 1:
+            b = torch.zeros_like(self.grad_bucket)
+            views, off = {}, 0
+            for name in self.names:
+                t = self.tensors[name]
+                views[name] = b[off:off + t.numel()].view(t.shape)
+                off += t.numel()
+            self._lanes.append((b, views))
+        return [self.grads()] + [v for _, v in self._lanes[:n - 1]]
+
+    def fold_lanes(self, n: int):
+        for b, _ in self._lanes[:n - 1]:
+            self.grad_bucket.add_(b)
 
     def grads(self) -> Dict[str, torch.Tensor]:
         return {n: t.grad for n, t in self.tensors.items()}
@@ -73,20 +93,32 @@ def default_loss(color: torch.Tensor, depth: torch.Tensor, Wc: torch.Tensor, Wd:
 
 def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: torch.Tensor, rasterizer_cls,
                       loss_fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor],
-                      rank: int = 0, world: int = 1, group=None, allreduce: bool = True) -> Dict[str, object]:
+                      rank: int = 0, world: int = 1, group=None, allreduce: bool = True,
+                      streams: int = 4) -> Dict[str, object]:
     """Render this rank's slice of `cameras`, backpropagate `loss_fn(color, depth, view_index)`, sum the
     parameter gradients over ranks.  Returns the step loss (summed over all views), per-view radii
-    counts and the number of views rendered locally."""
+    counts and the number of views rendered locally.
+
+    With the native rasterizer on a GPU the views are dealt round-robin onto `streams` CUDA streams: a
+    view's preprocess / sort / binning kernels (small grids, latency- and bandwidth-bound) then run
+    under another view's blend kernels (issue-bound), and the forward's one host wait for a view falls
+    while the other stream still has a backward queued.  Each stream adds into its own gradient bucket
+    (folded into the main one before the allreduce)."""
     params.zero_grad()
     mine = shard_views(len(cameras), rank, world)
-    loss_sum = torch.zeros((), dtype=torch.float32, device=params.flat.device)
+    dev = params.flat.device
     visible = []
     # the native rasterizer adds parameter gradients straight into the bucket slices (grad_sink);
     # any other rasterizer (the reference build, the CPU stand-in of the tests) goes through autograd
-    sink = params.grads() if getattr(rasterizer_cls, "supports_grad_sink", False) else None
-    for vi in mine:
+    use_sink = getattr(rasterizer_cls, "supports_grad_sink", False)
+    n_lanes = max(1, min(streams, len(mine))) if (use_sink and dev.type == "cuda") else 1
+    sinks = params.lane_sinks(n_lanes) if use_sink else [None]
+    losses = [torch.zeros((), dtype=torch.float32, device=dev) for _ in range(n_lanes)]
+
+    def one_view(vi: int, lane: int):
         cam = cameras[vi]
         settings = raster_settings(cam, params.sh_degree, bg, GaussianRasterizationSettings)
+        sink = sinks[lane]
         rast = rasterizer_cls(settings, grad_sink=sink) if sink is not None else rasterizer_cls(raster_settings=settings)
         means2D = torch.zeros_like(params.tensors["means3D"], requires_grad=True)
         color, radii, depth = rast(means3D=params.tensors["means3D"], means2D=means2D,
@@ -95,11 +127,40 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
                                    rotations=params.tensors["rotations"], cov3D_precomp=None)
         loss = loss_fn(color, depth, vi)
         loss.backward()
-        loss_sum += loss.detach()
+        losses[lane] += loss.detach()
         visible.append((vi, radii))
+
+    if n_lanes == 1:
+        for vi in mine:
+            one_view(vi, 0)
+    else:
+        cur = torch.cuda.current_stream(dev)
+        lanes = _lane_streams(dev, n_lanes)
+        for st in lanes:
+            st.wait_stream(cur)  # parameters, zeroed buckets
+        for j, vi in enumerate(mine):
+            with torch.cuda.stream(lanes[j % n_lanes]):
+                one_view(vi, j % n_lanes)
+        for st in lanes:
+            cur.wait_stream(st)
+        params.fold_lanes(n_lanes)
+    loss_sum = losses[0]
+    for extra in losses[1:]:
+        loss_sum = loss_sum + extra
     if world > 1 and allreduce:
         import torch.distributed as dist
 
         dist.all_reduce(params.grad_bucket, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)
     return {"loss": loss_sum, "views": mine, "radii": visible}
+
+
+_LANE_STREAMS: Dict[object, list] = {}
+
+
+def _lane_streams(dev: torch.device, n: int):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    pool = _LANE_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]

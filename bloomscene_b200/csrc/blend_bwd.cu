@@ -238,8 +238,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 			const int e = c0 + (int)lane;
 			bool hit = false;
 			if (e < cnt && e > warp_first_live) {
-				const float4 g = rec[e].geo;
-				hit = (g.x + g.z >= wx0) && (g.x - g.z <= wx1) && (g.y + g.w >= wy0) && (g.y - g.w <= wy1);
+				hit = block_may_contribute(rec[e].geo, rec[e].con, wx0, wx1, wy0, wy1);
 			}
 			uint32_t mask = __ballot_sync(0xffffffffu, hit);
 			while (mask) {

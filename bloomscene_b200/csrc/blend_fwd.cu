@@ -5,8 +5,8 @@
 // the CTA with three 16-byte cp.async gathers per record into a DOUBLE buffer: batch b+1 lands
 // while batch b is blended, the ids of batch b+2 are already in a register, and one barrier per
 // batch both publishes the new buffer and retires the old one.  Then every warp
-//   1. culls the batch against ITS pixel block: lane k tests record k's conservative alpha>=1/255
-//      bounding box (hx,hy from preprocess) -> ballot -> bit mask of records that can touch the warp;
+//   1. culls the batch against ITS pixel block: lane k tests whether record k's alpha >= 1/255 ellipse
+//      (threshold tau from preprocess) meets the block, exactly -> ballot -> bit mask of candidates;
 //   2. walks only the set bits, evaluating all 32 pixels for that record with warp-uniform smem
 //      broadcasts (LDS.128), and leaves as soon as all of its 32 pixels have saturated.
 // Culling is conservative: a skipped (pixel, record) pair is one the reference would `continue`
@@ -29,7 +29,7 @@ constexpr int BATCH = 256;
 
 __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdArgs a)
 {
-	__shared__ StagedRecord s_rec[2][BATCH]; // geo {x, y, hx, hy} | con {a, b, c, opacity} | col {r, g, b, depth}
+	__shared__ StagedRecord s_rec[2][BATCH]; // geo {x, y, tau, -} | con {a, b, c, opacity} | col {r, g, b, depth}
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -72,8 +72,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 			const int e = c0 + (int)lane;
 			bool hit = false;
 			if (e < cnt) {
-				const float4 g = rec[e].geo;
-				hit = (g.x + g.z >= wx0) && (g.x - g.z <= wx1) && (g.y + g.w >= wy0) && (g.y - g.w <= wy1);
+				hit = block_may_contribute(rec[e].geo, rec[e].con, wx0, wx1, wy0, wy1);
 			}
 			uint32_t mask = __ballot_sync(0xffffffffu, hit);
 			while (mask) {

@@ -5,7 +5,7 @@
 //   check_frustum_kernel   <- reference checkFrustum          (rasterizer_impl.cu:54-66)
 //
 // What differs from the reference (layout / scheduling only — the arithmetic keeps its shapes):
-//   * one packed 48-byte blend record per Gaussian {x,y,hx,hy | conic a,b,c,opacity | r,g,b,depth}
+//   * one packed 48-byte blend record per Gaussian {x,y,tau,0 | conic a,b,c,opacity | r,g,b,depth}
 //     instead of five separate arrays, so the blend kernels gather three aligned float4s;
 //   * SH coefficients of the *visible* Gaussians of a block are staged through shared memory with
 //     coalesced 128-bit streaming loads (row pitch 13 float4 -> conflict-free per-thread reads);
@@ -13,8 +13,8 @@
 //   * the per-Gaussian tile rectangle is stored packed (8 B) and the grid-wide instance count R is
 //     accumulated here with one integer atomic per block, so the host can read R while the depth
 //     sort is already running;
-//   * hx,hy: a conservative bounding box of the region where this Gaussian's alpha can reach 1/255
-//     (used by the blend kernels for warp-level culling; see cull_extent()).
+//   * tau: a conservative bound on q = d^T conic d beyond which this Gaussian's alpha cannot reach
+//     1/255 (used by the blend kernels for warp-level culling; see cull_tau()).
 #include "common.cuh"
 #include "gaussian_math.cuh"
 #include "kernels.h"
@@ -124,34 +124,33 @@ __device__ __forceinline__ bool compute_geometry(const float3 p_orig, const floa
 	return true;
 }
 
-// Conservative half-extents (in pixels) of {pixel : the reference blend would NOT `continue`}.
-// The blend keeps a pair only if alpha = min(0.99, o*exp(power)) >= 1/255 with
-// power = -0.5 (a dx^2 + c dy^2) - b dx dy evaluated in fp32 (forward.cu:416-429), i.e. only if
-// f(d) = d^T Q d <= tau := 2 ln(255 o) up to fp32 evaluation noise.  The box of that ellipse is
-// |dx| <= sqrt(tau Q^-1_xx), |dy| <= sqrt(tau Q^-1_yy), computed here in fp64 from the SAME fp32
-// conic the blend uses, with tau inflated by a bound on the fp32 evaluation error over every pixel
-// this Gaussian can meet (|d| <= radius + tile).  Where no bound can be given the box is infinite
-// (no culling), where opacity < 1/255 it is empty (alpha <= o always).
-__device__ __forceinline__ float2 cull_extent(const float3 conic, float opacity, int radius)
+// Conservative threshold for the blend kernels' warp-level culling (block_may_contribute(), common.cuh).
+// The reference blend keeps a (pixel, Gaussian) pair only if alpha = min(0.99, o*exp(power)) >= 1/255
+// with power = -0.5 (a dx^2 + c dy^2) - b dx dy evaluated in fp32 (forward.cu:416-429), i.e. only if
+// q(d) = d^T Q d <= tau := 2 ln(255 o) up to fp32 evaluation noise.  A warp skips a Gaussian when the
+// minimum of q over its pixel block exceeds the value returned here: tau inflated by a bound on the
+// fp32 evaluation error of q (the reference's evaluation at the pixel AND the culling test's own at the
+// block's closest point) over every offset this Gaussian can meet (|d| <= radius + tile), plus an
+// absolute and a relative margin.  Computed in fp64 from the SAME fp32 conic the blend uses.
+// +inf (never cull) where no bound can be given, -inf (always cull) where opacity < 1/255 (alpha <= o).
+__device__ __forceinline__ float cull_tau(const float3 conic, float opacity, int radius)
 {
 	const float inf = __int_as_float(0x7f800000);
 	if (opacity < 1.0f / 255.0f)
-		return make_float2(-inf, -inf);
+		return -inf;
 	if (!(opacity <= 3.0e38f)) // NaN / inf opacity: let the blend decide
-		return make_float2(inf, inf);
+		return inf;
 	const double a = conic.x, b = conic.y, c = conic.z;
 	const double det = a * c - b * b;
 	if (!(det > 0.0) || !(a > 0.0) || !(c > 0.0))
-		return make_float2(inf, inf);
+		return inf;
 	const double dmax = (double)radius + (double)(TILE_X + 1);
 	const double eval_err = 8.0 * 5.9604644775390625e-08 * (fabs(a) + fabs(c) + 2.0 * fabs(b)) * dmax * dmax;
 	double tau = 2.0 * log(255.0 * (double)opacity);
-	tau = (tau + eval_err + 1e-4) * (1.0 + 1e-5);
-	const double hx = sqrt(tau * c / det);
-	const double hy = sqrt(tau * a / det);
-	if (!(hx < 1e30) || !(hy < 1e30))
-		return make_float2(inf, inf);
-	return make_float2((float)(hx * (1.0 + 1e-6) + 1e-3), (float)(hy * (1.0 + 1e-6) + 1e-3));
+	tau = (tau + 4.0 * eval_err + 1e-4) * (1.0 + 1e-5);
+	if (!(tau < 1e30))
+		return inf;
+	return (float)(tau * (1.0 + 1e-6) + 1e-6);
 }
 
 // ---- K1 -----------------------------------------------------------------------------------------
@@ -269,9 +268,9 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	if (idx < a.P) {
 		if (visible) {
 			const float opacity = __ldg(a.opacities + idx);
-			const float2 h = cull_extent(g.conic, opacity, g.radius);
+			const float tau = cull_tau(g.conic, opacity, g.radius);
 			float4* rec = a.records + 3 * (size_t)idx;
-			rec[0] = make_float4(g.xy.x, g.xy.y, h.x, h.y);
+			rec[0] = make_float4(g.xy.x, g.xy.y, tau, 0.f);
 			rec[1] = make_float4(g.conic.x, g.conic.y, g.conic.z, opacity);
 			rec[2] = make_float4(rgb.x, rgb.y, rgb.z, g.depth);
 			a.radii[idx] = g.radius;

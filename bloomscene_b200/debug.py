@@ -33,7 +33,7 @@ def state_views(_C, geom: torch.Tensor, binning: torch.Tensor, image: torch.Tens
     }
     rec = out["records"]
     out["means2D"] = rec[:, 0:2]
-    out["cull_extent"] = rec[:, 2:4]
+    out["cull_tau"] = rec[:, 2]
     out["conic_opacity"] = rec[:, 4:8]
     out["rgb"] = rec[:, 8:11]
     out["depths"] = rec[:, 11]

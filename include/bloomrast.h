@@ -173,7 +173,7 @@ int brs_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in,
  * each buffer; strides in bytes). */
 typedef struct brs_layout {
 	/* geom */
-	size_t geom_records;   /* float4[3*P]: {x,y,hx,hy} {conic a,b,c,opacity} {r,g,b,depth} */
+	size_t geom_records;   /* float4[3*P]: {x,y,tau,0} {conic a,b,c,opacity} {r,g,b,depth} */
 	size_t geom_depth_key; /* u32[P]: float bits of view-space depth, 0xFFFFFFFF when culled */
 	size_t geom_rect;      /* u32[2*P]: (x0 | x1<<16), (y0 | y1<<16) tile rectangle */
 	size_t geom_order;     /* u32[P]: Gaussian ids sorted by (depth, id) */

@@ -43,6 +43,14 @@ CONFIG_NAME = "E"
 N_VIEWS = 64
 
 
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch at config C, read from the
+# `ncu --set full` captures summarised under profiles/ (refreshed whenever a blend kernel changes).
+NCU_TRAFFIC = {
+    "blend_bwd": {"bytes": int((112.7 + 8.564) * 1e6), "source": "profiles/r01h_ncu_blend.md"},
+    "blend_fwd": {"bytes": int((76.59 + 25.04) * 1e6), "source": "profiles/r01h_ncu_blend.md"},
+}
+
+
 # ---- clocks --------------------------------------------------------------------------------------
 
 class ClockSampler:
@@ -111,7 +119,7 @@ def stage_model(P, V, R, R1, M, npix, ntile, E, C, Eb):
     R1 = (supertile, Gaussian) instances, the only thing the coarse level sorts."""
     return {
         "preprocess": ("hbm", 52 * P + (12 * M + 67) * V),
-        "depth_sort": ("hbm", (4 + 16 * 4) * P),  # one histogram read + 4 passes reading and writing 8-byte pairs
+        "depth_sort": ("hbm", (4 + 16 * 3) * P),  # one histogram read + 3 passes of 8-byte pairs (23-24 significant key bits)
         "coarse_emit": ("hbm", 4 * P + 8 * V + 8 * R1),
         "coarse_sort": ("hbm", (4 + 16) * R1),  # histogram read + one pass of 8-byte pairs (<= 256 supertiles)
         "fine_bin": ("hbm", 2 * (4 + 8) * R1 + 4 * R + 16 * ntile),  # count + scatter passes read id + rect; ids written once
@@ -327,8 +335,19 @@ def main():
             t_roof += (work / (peak * (1e9 if bound == "hbm" else 1e12))) * 1e3
         dom = max(stages, key=lambda k: stages[k]["ms"])
         d = stages[dom]
+        # DRAM bytes of the dominant kernel per launch, from the committed `ncu --set full` capture
+        traffic = NCU_TRAFFIC.get(dom, {}).get("bytes")
+        # the same kernel against the HBM roof: algorithmic floor bytes of SURVEY.md 8(d) / measured time
+        hbm_floor = {"blend_bwd": 4 * st["R"] + 72 * st["V"] + 20 * W * H, "blend_fwd": 4 * st["R"] + 40 * st["V"] + 24 * W * H}.get(dom)
+        hbm_view = None
+        if hbm_floor is not None:
+            gbs = hbm_floor / (d["ms"] * 1e-3) / 1e9
+            hbm_view = {"algorithmic_bytes": int(hbm_floor), "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(gbs / hbm_peak, 4),
+                        "note": "far below the HBM roof: the kernel is bound by FP32/ALU issue slots, not by memory"}
         out["roofline"] = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                           "frac": d["frac"], "traffic": None,
+                           "frac": d["frac"], "traffic": traffic, "traffic_source": NCU_TRAFFIC.get(dom, {}).get("source"),
+                           "hbm_view": hbm_view,
                            "peak_source": ("live dependent-FFMA micro-benchmark brs_probe_fp32_tflops()" if d["bound"] == "fp32" else hbm_src),
                            "note": "the dominant kernel is FP32-pipe bound (no dense contraction on this path, tensor cores "
                                    "not applicable); algorithmic flops = 21*E_b + 70*C with E_b, C counted by brs_count_pairs",

@@ -4,12 +4,14 @@
 // sub-allocator (rasterizer_impl.h:21-73, rasterizer_impl.cu:155-194).
 //
 // Stage order of brs_forward (all on the caller's stream):
-//   memset(header) -> preprocess -> [async copy of R, R1 to pinned host memory + event]
-//   -> depth sort (4 radix passes over P keys; does not need R, so the GPU stays busy while the host
-//      waits for the event) -> host: wait R/R1, allocate binning/scratch -> coarse binning (scan +
-//      emit of supertile instances, one radix pass on the supertile id) -> fine binning (count, scan,
-//      scatter: point_list and tile ranges) -> blend.
-// brs_backward: memset(accumulator) -> blend backward -> fused preprocess backward.  No host sync.
+//   memset(header) -> preprocess -> [async copy of R, R1 and the depth-key range to pinned host + event]
+//   -> depth sort pass 1 (low 8 key bits of P keys; needs none of them, so the GPU stays busy while the
+//      host waits for the event) -> host: wait, allocate binning/scratch, choose the remaining digit
+//      widths from the key range -> depth sort passes 2..k -> coarse binning (scan + emit of supertile
+//      instances, one radix pass on the supertile id) -> fine binning (count, scan, scatter:
+//      point_list and tile ranges) -> blend.
+// brs_backward: memset(accumulator) -> blend backward -> fused preprocess backward (plain or
+// accumulate mode, see brs_grads).  No host sync.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>

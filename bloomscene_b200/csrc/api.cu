@@ -16,6 +16,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -98,6 +101,47 @@ struct StageScope {
 		}
 	}
 };
+
+// Companion stream for the blend kernels.  The blend kernels are large, issue-bound grids; everything
+// else on the path is small or bandwidth-bound.  When the caller runs several views on several streams
+// (view-sharded step), a blend grid monopolises the block scheduler and the other views' small kernels
+// wait for its tail.  If the caller's stream has a HIGHER priority than the device's lowest, the blend
+// kernels are therefore launched on a lowest-priority companion stream, fenced by events on both
+// sides: stream order as the caller sees it is unchanged, but pending blocks of the (higher-priority)
+// preprocess / sort / binning kernels of other views are dispatched ahead of the blend's remaining
+// blocks and run underneath it.  Callers on default-priority streams get no companion.
+struct Companion {
+	cudaStream_t stream = nullptr;
+	cudaEvent_t before = nullptr, after = nullptr;
+};
+std::mutex g_companion_mutex;
+std::map<std::pair<int, cudaStream_t>, Companion> g_companions;
+int g_companion_enabled = 1;
+
+// Returns nullptr when the blend should simply run on `stream`.
+Companion* companion_for(cudaStream_t stream)
+{
+	if (!g_companion_enabled || t_timer.enabled || stream == nullptr)
+		return nullptr;
+	int least = 0, greatest = 0, prio = 0, dev = 0;
+	if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess || least == greatest)
+		return nullptr;
+	if (cudaStreamGetPriority(stream, &prio) != cudaSuccess || prio >= least) // numerically lower = higher priority
+		return nullptr;
+	if (cudaGetDevice(&dev) != cudaSuccess)
+		return nullptr;
+	std::lock_guard<std::mutex> lock(g_companion_mutex);
+	Companion& c = g_companions[std::make_pair(dev, stream)];
+	if (c.stream == nullptr) {
+		if (cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, least) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&c.before, cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&c.after, cudaEventDisableTiming) != cudaSuccess) {
+			c = Companion{};
+			return nullptr;
+		}
+	}
+	return &c;
+}
 
 inline int fail_cuda(cudaError_t e)
 {
@@ -289,6 +333,14 @@ int brs_state_layout(int P, int R, int W, int H, brs_layout* out)
 }
 
 void brs_stage_timing(int enable) { t_timer.enabled = enable != 0; }
+
+int brs_blend_companion_stream(int enable)
+{
+	const int old = g_companion_enabled;
+	if (enable >= 0)
+		g_companion_enabled = enable != 0;
+	return old;
+}
 
 int brs_stage_times(float* ms, int* calls)
 {
@@ -543,7 +595,15 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	ba.n_contrib = n_contrib;
 	ba.out_color = out_color;
 	ba.out_depth = out_depth;
-	BRS_STAGE(BRS_STAGE_BLEND_FWD, launch_blend_forward(ba, stream), debug, stream);
+	if (Companion* c = debug ? nullptr : companion_for(stream)) {
+		BRS_CUDA(cudaEventRecord(c->before, stream));
+		BRS_CUDA(cudaStreamWaitEvent(c->stream, c->before, 0));
+		BRS_CUDA(launch_blend_forward(ba, c->stream));
+		BRS_CUDA(cudaEventRecord(c->after, c->stream));
+		BRS_CUDA(cudaStreamWaitEvent(stream, c->after, 0));
+	} else {
+		BRS_STAGE(BRS_STAGE_BLEND_FWD, launch_blend_forward(ba, stream), debug, stream);
+	}
 	return BRS_OK;
 }
 
@@ -606,7 +666,15 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 		bb.n_contrib = reinterpret_cast<const uint32_t*>(image + il.n_contrib);
 		bb.dL_dpixels = dL_dout_color;
 		bb.accum = accum;
-		BRS_STAGE(BRS_STAGE_BLEND_BWD, launch_blend_backward(bb, stream), debug, stream);
+		if (Companion* c = debug ? nullptr : companion_for(stream)) {
+			BRS_CUDA(cudaEventRecord(c->before, stream));
+			BRS_CUDA(cudaStreamWaitEvent(c->stream, c->before, 0));
+			BRS_CUDA(launch_blend_backward(bb, c->stream));
+			BRS_CUDA(cudaEventRecord(c->after, c->stream));
+			BRS_CUDA(cudaStreamWaitEvent(stream, c->after, 0));
+		} else {
+			BRS_STAGE(BRS_STAGE_BLEND_BWD, launch_blend_backward(bb, stream), debug, stream);
+		}
 	}
 
 	PreprocessBwdArgs pb{};

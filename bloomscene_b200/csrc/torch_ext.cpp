@@ -475,4 +475,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("state_layout", &StateLayout);
 	m.def("launch_count", [](bool reset) { return brs_launch_count(reset ? 1 : 0); }, pybind11::arg("reset") = false);
 	m.def("version", []() { return brs_version(); });
+	m.def("blend_companion_stream", [](int enable) { return brs_blend_companion_stream(enable); }, pybind11::arg("enable") = -1);
 }

@@ -162,5 +162,7 @@ def _lane_streams(dev: torch.device, n: int):
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     pool = _LANE_STREAMS.setdefault(key, [])
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=dev))
+        # high priority: the library then moves its blend kernels to a lowest-priority companion stream,
+        # so the small kernels of one view are dispatched underneath another view's blend grid
+        pool.append(torch.cuda.Stream(device=dev, priority=-1))
     return pool[:n]

@@ -210,6 +210,14 @@ enum {
 };
 /* When enabled, every stage is bracketed by CUDA events on the call's stream (per thread). */
 void brs_stage_timing(int enable);
+
+/* Scheduling option (no reference counterpart).  When the caller's stream has a higher priority than
+ * the device's lowest, brs_forward / brs_backward launch their blend kernels on an internal
+ * lowest-priority companion stream fenced by events on both sides, so that other views' small
+ * preprocess / sort / binning kernels (on other high-priority streams) are dispatched ahead of a
+ * blend grid's remaining blocks.  Stream order as seen by the caller is unchanged.  enable: 1 / 0 to
+ * set, -1 to query; returns the previous setting (default 1).  No effect on default-priority streams. */
+int brs_blend_companion_stream(int enable);
 /* Synchronises the recorded events; adds the accumulated milliseconds per stage into ms[BRS_NUM_STAGES]
  * and the number of timed launches per stage into calls[BRS_NUM_STAGES] (either may be NULL),
  * then clears the accumulators. */

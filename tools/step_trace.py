@@ -48,6 +48,8 @@ def main():
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
         torch.cuda.synchronize()
+    if os.environ.get("STEP_TRACE_JSON"):
+        prof.export_chrome_trace(os.environ["STEP_TRACE_JSON"])
     rows = []
     for ev in prof.key_averages():
         t = getattr(ev, "device_time_total", None)

@@ -491,7 +491,7 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 
 	// R, R1 and the depth-key range leave for the host now.  The first radix pass of the depth sort (low
 	// 8 key bits) needs none of them and keeps the GPU busy during the host round trip.
-	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	BRS_CUDA(cudaEventRecord(t_slot.event, stream));
 
 	char* scratch1 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, depth_scratch_bytes(P)));
@@ -502,13 +502,17 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	uint32_t* first_keys = reinterpret_cast<uint32_t*>(scratch1 + pb);
 	uint32_t* first_vals = reinterpret_cast<uint32_t*>(scratch1 + 2 * pb);
 	char* depth_sort_scratch = scratch1 + 3 * pb;
+	// culled Gaussians (key 0xFFFFFFFF) are dropped here: the later passes and the emission only see
+	// the V visible ones
 	BRS_STAGE(BRS_STAGE_DEPTH_SORT,
-	          sort_pass(depth_key, nullptr, first_keys, first_vals, (size_t)P, 0u, 0, 8, depth_sort_scratch, stream), debug,
-	          stream);
+	          sort_pass(depth_key, nullptr, first_keys, first_vals, (size_t)P, 0u, 0, 8, depth_sort_scratch, stream, true,
+	                    DEPTH_KEY_CULLED),
+	          debug, stream);
 
 	BRS_CUDA(cudaEventSynchronize(t_slot.event)); // the one host wait (reference: rasterizer_impl.cu:282)
 	const uint32_t R = t_slot.pinned[0], R1 = t_slot.pinned[1];
 	const uint32_t key_min = ~t_slot.pinned[2], key_max = t_slot.pinned[3];
+	const uint32_t V = t_slot.pinned[4]; // visible Gaussians = entries that survived the first pass
 	if (R > (1u << 30))
 		return BRS_ERR_UNSUPPORTED;
 	state->num_rendered = (int)R;
@@ -516,8 +520,10 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	// Remaining passes of the depth sort.  Visible keys lie in [key_min, key_max]; subtracting a bias
 	// that is a multiple of 256 keeps the first pass's digit, preserves order and ties, and leaves only
 	// bit_length(key_max - bias) significant bits (23-24 for a scene a few units deep instead of 32).
-	// Culled Gaussians (key 0xFFFFFFFF) wrap to arbitrary places in `order`; they emit nothing.
-	{
+	// `order` ends up holding the V visible ids.  A visible Gaussian cannot carry the culled marker as
+	// its depth bits: 0xFFFFFFFF is a NaN pattern the GPU's arithmetic never produces (its NaN is
+	// 0x7FFFFFFF).
+	if (V > 0) {
 		const uint32_t bias = key_min <= key_max ? (key_min & ~0xFFu) : 0u;
 		const uint32_t span = key_min <= key_max ? key_max - bias : 0u;
 		int nbits = 8;
@@ -536,7 +542,7 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 			const bool to_out = ((passes - 1 - p) & 1) == 0;
 			uint32_t* ko = to_out ? sorted_depth : tmp_keys;
 			uint32_t* vo = to_out ? order : tmp_vals;
-			BRS_STAGE(BRS_STAGE_DEPTH_SORT, sort_pass(kin, vin, ko, vo, (size_t)P, bias, shift, bits, depth_sort_scratch, stream),
+			BRS_STAGE(BRS_STAGE_DEPTH_SORT, sort_pass(kin, vin, ko, vo, (size_t)V, bias, shift, bits, depth_sort_scratch, stream),
 			          debug, stream);
 			kin = ko;
 			vin = vo;
@@ -567,7 +573,7 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 
 		if (R1 > 0) {
 			BRS_STAGE(BRS_STAGE_COARSE_EMIT,
-			          launch_emit(order, rect, (size_t)P, ST_SHIFT, ns_x, cell_keys, cell_ids, (size_t)R1, emit_scratch,
+			          launch_emit(order, rect, (size_t)V, ST_SHIFT, ns_x, cell_keys, cell_ids, (size_t)R1, emit_scratch,
 			                      stream),
 			          debug, stream);
 			BRS_STAGE(BRS_STAGE_COARSE_SORT,

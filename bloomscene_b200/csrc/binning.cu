@@ -94,7 +94,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 // ---- upsweep: digit counts of one tile ------------------------------------------------------------
 __global__ void __launch_bounds__(SORT_THREADS)
     upsweep_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t bias, int shift, int bits, uint32_t tiles,
-                   uint32_t* __restrict__ table)
+                   uint32_t* __restrict__ table, uint32_t drop_key, int drop)
 {
 	__shared__ uint32_t s_cnt[RADIX_MAX];
 	const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 	}
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
-		const bool valid = (tid + i * SORT_THREADS) < valid_count;
+		const bool valid = (tid + i * SORT_THREADS) < valid_count && !(drop && key[i] == drop_key);
 		const uint32_t d = ((key[i] - bias) >> shift) & mask;
 		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
 		if (valid && (uint32_t)(__ffs(peers) - 1) == lane)
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(SORT_THREADS) scan_kernel(uint32_t* __restrict
 __global__ void __launch_bounds__(SORT_THREADS)
     downsweep_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint32_t* __restrict__ kout,
                      uint32_t* __restrict__ vout, uint32_t n, uint32_t bias, int shift, int bits, uint32_t tiles,
-                     const uint32_t* __restrict__ table, const uint32_t* __restrict__ totals)
+                     const uint32_t* __restrict__ table, const uint32_t* __restrict__ totals, uint32_t drop_key, int drop)
 {
 	__shared__ uint32_t s_cnt[SORT_WARPS][RADIX_MAX];
 	__shared__ uint32_t s_keys[SORT_TILE];
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 	uint32_t* my_cnt = s_cnt[warp];
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
-		const bool valid = (wbase + i * 32) < valid_count;
+		const bool valid = (wbase + i * 32) < valid_count && !(drop && key[i] == drop_key);
 		const uint32_t d = ((key[i] - bias) >> shift) & mask;
 		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
 		const int leader = __ffs(peers) - 1;
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(SORT_THREADS)
 			total += c;
 		}
 	}
-	uint32_t dummy;
-	const uint32_t digit_start = block_exclusive_scan_256(total, s_warp, dummy);
+	uint32_t dummy, kept; // kept = keys of this tile that take part (all valid ones unless `drop`)
+	const uint32_t digit_start = block_exclusive_scan_256(total, s_warp, kept);
 	const uint32_t bin_base = block_exclusive_scan_256(digit_total, s_warp, dummy);
 	if (tid < radix) {
 		s_digit_start[tid] = digit_start;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
 		const uint32_t li = wbase + i * 32;
-		if (li < valid_count) {
+		if (li < valid_count && !(drop && key[i] == drop_key)) {
 			const uint32_t d = ((key[i] - bias) >> shift) & mask;
 			const uint32_t pos = s_digit_start[d] + s_cnt[warp][d] + rank[i];
 			s_keys[pos] = key[i];
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 #pragma unroll
 	for (int i = 0; i < SORT_ITEMS; i++) {
 		const uint32_t j = tid + i * SORT_THREADS;
-		if (j < valid_count) {
+		if (j < kept) {
 			const uint32_t k = s_keys[j];
 			const uint32_t g = s_goff[((k - bias) >> shift) & mask] + j;
 			kout[g] = k;
@@ -279,16 +279,17 @@ void sort_tmp_buffers(void* scratch, size_t n, uint32_t** tmp_keys, uint32_t** t
 }
 
 cudaError_t sort_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout, size_t n, uint32_t bias,
-                      int shift, int bits, void* scratch, cudaStream_t stream)
+                      int shift, int bits, void* scratch, cudaStream_t stream, bool drop, uint32_t drop_key)
 {
 	if (n == 0)
 		return cudaSuccess;
 	SortScratch s = carve_sort_scratch(scratch, n);
 	const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
-	upsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, (uint32_t)n, bias, shift, bits, tiles, s.table);
+	upsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, (uint32_t)n, bias, shift, bits, tiles, s.table, drop_key,
+	                                                   drop ? 1 : 0);
 	scan_kernel<<<1u << bits, SORT_THREADS, 0, stream>>>(s.table, tiles, s.totals);
 	downsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, (uint32_t)n, bias, shift, bits, tiles,
-	                                                     s.table, s.totals);
+	                                                     s.table, s.totals, drop_key, drop ? 1 : 0);
 	count_launch();
 	count_launch();
 	count_launch();

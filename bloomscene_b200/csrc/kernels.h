@@ -31,7 +31,8 @@ struct PreprocessArgs {
 	float4* records;      // [3P]
 	uint32_t* depth_key;  // [P]
 	uint2* rect;          // [P]
-	uint32_t* total_tiles; // [4], pre-zeroed: R = tile instances, R1 = supertile instances, max(~depth bits), max(depth bits) over visible
+	uint32_t* total_tiles; // [5], pre-zeroed: R = tile instances, R1 = supertile instances, max(~depth bits),
+	                       // max(depth bits) over visible, V = number of visible Gaussians
 };
 cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream);
 
@@ -64,8 +65,11 @@ size_t sort_scratch_bytes(size_t n);
 cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                        size_t n, int begin_bit, int end_bit, void* scratch, cudaStream_t stream);
 // One stable pass on the digit ((key - bias) >> shift) & ((1 << bits) - 1), bits <= 8; in != out.
+// With `drop`, keys equal to `drop_key` are left out: the output then holds only the other keys
+// (compacted, still stable) and the caller continues with the smaller count.
 cudaError_t sort_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
-                      uint32_t bias, int shift, int bits, void* scratch, cudaStream_t stream);
+                      uint32_t bias, int shift, int bits, void* scratch, cudaStream_t stream, bool drop = false,
+                      uint32_t drop_key = 0);
 // The ping-pong buffers inside a sort scratch area (n keys + n values).
 void sort_tmp_buffers(void* scratch, size_t n, uint32_t** tmp_keys, uint32_t** tmp_vals);
 

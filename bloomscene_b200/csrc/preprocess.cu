@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	extern __shared__ float4 s_dyn[]; // SH staging (only when a.shs != nullptr)
 	__shared__ float s_cam[36];
 	__shared__ uint32_t s_vis[PRE_THREADS / 32];
-	__shared__ uint32_t s_tiles[4][PRE_THREADS / 32];
+	__shared__ uint32_t s_tiles[5][PRE_THREADS / 32];
 
 	stage_camera(s_cam, a.viewmatrix, a.projmatrix, a.campos);
 	__syncthreads();
@@ -299,9 +299,10 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 		s_tiles[1][warp] = cells;
 		s_tiles[2][warp] = inv_min;
 		s_tiles[3][warp] = key_max;
+		s_tiles[4][warp] = (uint32_t)__popc(vis_mask);
 	}
 	__syncthreads();
-	if (threadIdx.x < 2) {
+	if (threadIdx.x < 2 || threadIdx.x == 4) {
 		uint32_t sum = 0;
 #pragma unroll
 		for (int w = 0; w < PRE_THREADS / 32; w++)

@@ -194,8 +194,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 		tile_max = max(tile_max, (int)s_max[w]);
 	const int n = min((int)(range.y - range.x), tile_max);
 
-	float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f;
-	float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
+	float beta = 0.f, last_alpha = 0.f, last_cd = 0.f;
 	float bg_dot_dpixel = 0.f;
 	bg_dot_dpixel += __ldg(a.bg + 0) * dpx0;
 	bg_dot_dpixel += __ldg(a.bg + 1) * dpx1;
@@ -269,17 +268,14 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 					T = T * rcp;
 					u_ = alpha * T; // dchannel_dcolor
 
-					const float om = 1.f - last_alpha;
-					accum_rec0 = last_alpha * last_c0 + om * accum_rec0;
-					accum_rec1 = last_alpha * last_c1 + om * accum_rec1;
-					accum_rec2 = last_alpha * last_c2 + om * accum_rec2;
-					last_c0 = col.x;
-					last_c1 = col.y;
-					last_c2 = col.z;
-					float dL_dalpha = (col.x - accum_rec0) * dpx0;
-					dL_dalpha += (col.y - accum_rec1) * dpx1;
-					dL_dalpha += (col.z - accum_rec2) * dpx2;
-					dL_dalpha *= T;
+					// reference backward.cu:519-533 keeps, per channel, the colour accumulated BEHIND this record
+					// (accum_rec) and sums (c - accum_rec) * dL_dpixel over the channels.  Only that sum is
+					// needed, so the recurrence runs on its projection: beta = accum_rec . dL_dpixel and
+					// cd = colour . dL_dpixel are scalars.
+					beta = fmaf(last_alpha, last_cd - beta, beta);
+					const float cd = fmaf(col.z, dpx2, fmaf(col.y, dpx1, col.x * dpx0));
+					float dL_dalpha = (cd - beta) * T;
+					last_cd = cd;
 					last_alpha = alpha;
 					dL_dalpha += neg_Tf_bg * rcp;
 					w_ = G * dL_dalpha;

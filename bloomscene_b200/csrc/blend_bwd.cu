@@ -34,7 +34,7 @@ constexpr int BLEND_THREADS = TILE_X * TILE_Y;
 constexpr int BLEND_WARPS = BLEND_THREADS / 32;
 constexpr int BATCH = 256;
 constexpr int GROUP = 8;         // contributing records staged per warp between flushes (8 records x 4 rows = 32 lanes)
-constexpr int STAGE_STRIDE = 68; // floats per staged record: w[32] | u[32] | 4 pad -> the flush's LDS.128 are conflict-free
+constexpr int STAGE_STRIDE = 68; // floats per staged record: w[32] | u[32] | batch slot + 3 pad -> the flush's LDS.128 are conflict-free
 
 __device__ __forceinline__ float rcp_approx(float x)
 {
@@ -50,7 +50,7 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 
 // Flush `cnt` (<= GROUP) staged records of this warp.  Lane (r = lane >> 2, q = lane & 3) owns
 // record r and the q-th row (8 pixels) of the warp's pixel block.
-__device__ __forceinline__ void flush_group(const float* __restrict__ stage, const uint32_t* __restrict__ slots, int cnt,
+__device__ __forceinline__ void flush_group(const float* __restrict__ stage, int cnt,
                                             const StagedRecord* __restrict__ rec, const uint32_t* __restrict__ s_id,
                                             const float* __restrict__ s_dpx, float bxf, float byf, uint32_t lane,
                                             float* __restrict__ accum)
@@ -64,7 +64,7 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, con
 		v[i] = 0.f;
 	uint32_t id = 0;
 	if (live) {
-		const uint32_t idx = slots[r];
+		const uint32_t idx = (uint32_t)__float_as_int(stage[r * STAGE_STRIDE + 64]);
 		const float2 g = *reinterpret_cast<const float2*>(&rec[idx].geo);
 		const float4 con = rec[idx].con;
 		id = s_id[idx];
@@ -149,7 +149,6 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	__shared__ uint32_t s_ids[2][BATCH];
 	__shared__ __align__(16) float s_stage[BLEND_WARPS][GROUP * STAGE_STRIDE];
 	__shared__ __align__(16) float s_dpx[BLEND_WARPS][3 * 32];
-	__shared__ uint32_t s_slot[BLEND_WARPS][GROUP];
 	__shared__ uint32_t s_max[BLEND_WARPS];
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -202,9 +201,9 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	const float neg_Tf_bg = -T_final * bg_dot_dpixel;
 
 	float* const stage = s_stage[warp];
-	uint32_t* const slots = s_slot[warp];
 	const float* const dpx_rows = s_dpx[warp];
 	int staged = 0;
+	float* st = stage + lane; // this lane's column of the next free staging slot
 
 	// batches walk the list backwards: slot s of the batch at `base` holds list position n-1-(base+s).
 	// Double-buffered cp.async staging as in the forward: batch b+1 lands while batch b is processed.
@@ -280,21 +279,23 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 					dL_dalpha += neg_Tf_bg * rcp;
 					w_ = G * dL_dalpha;
 				}
-				float* st = stage + staged * STAGE_STRIDE;
-				st[lane] = w_;
-				st[32 + lane] = u_;
+				st[0] = w_;
+				st[32] = u_;
 				if (lane == 0)
-					slots[staged] = (uint32_t)idx;
+					st[64] = __int_as_float(idx); // the record's batch slot rides in the row's padding
+				st += STAGE_STRIDE;
 				if (++staged == GROUP) {
-					flush_group(stage, slots, GROUP, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
+					flush_group(stage, GROUP, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 					staged = 0;
+					st = stage + lane;
 				}
 			}
 		}
 		// staged slots refer to this batch's shared records: flush before they are overwritten
 		if (staged) {
-			flush_group(stage, slots, staged, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
+			flush_group(stage, staged, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 			staged = 0;
+			st = stage + lane;
 		}
 	}
 }

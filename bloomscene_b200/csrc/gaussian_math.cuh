@@ -34,9 +34,23 @@ __device__ __forceinline__ void compute_cov3d(const v3 scale, float mod, const f
 	cov3D[5] = Sigma.c[2].z;
 }
 
-// reference forward.cu:20-71.  `sh` points at this Gaussian's coefficients, `pitch` floats apart per
-// coefficient triple (3 for dense rows).  Returns the un-clamped colour; the caller clamps.
-__device__ __forceinline__ v3 eval_sh(int deg, const v3 pos, const v3 campos, const float* sh)
+// A Gaussian's SH row as it sits in shared memory (float4 pieces).  operator[] with a compile-time
+// index is one LDS.128 (merged by the compiler with its neighbours) plus a register pick, so the row
+// is pulled into registers a few coefficients at a time instead of living there as 48 floats.
+struct ShRowView {
+	const float4* row;
+	__device__ __forceinline__ float operator[](int i) const
+	{
+		const float4 v = row[i >> 2];
+		const int c = i & 3;
+		return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+	}
+};
+
+// reference forward.cu:20-71.  `sh` indexes this Gaussian's coefficients (3 floats per coefficient,
+// dense): a `const float*` or a ShRowView.  Returns the un-clamped colour; the caller clamps.
+template <class SH>
+__device__ __forceinline__ v3 eval_sh(int deg, const v3 pos, const v3 campos, const SH sh)
 {
 	v3 dir = pos - campos;
 	dir = dir / length3(dir);

@@ -139,6 +139,7 @@ struct PreprocessBwdArgs {
 	float tan_fovx, tan_fovy, focal_x, focal_y;
 	const float* accum; // [P][12] from the blend backward
 	int accumulate;     // 0: every output element is written; 1: see brs_grads.accumulate
+	int fact_offset;    // (set by the launcher) float offset of the basis-factor rows in dynamic shared memory
 	// outputs
 	float* dL_dmeans2D;   // [P,3]
 	float* dL_dcolors;    // [P,3]

@@ -42,7 +42,8 @@ __device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv)
 
 // reference backward.cu:20-139.  `sh` = this Gaussian's coefficients (constant indices only),
 // fact[0..15] receive dRGB/dsh_k, returns dL/dmean contribution through the view direction.
-__device__ __forceinline__ float3 sh_backward(int deg, const v3 pos, const v3 campos, const float* sh,
+template <class SH>
+__device__ __forceinline__ float3 sh_backward(int deg, const v3 pos, const v3 campos, const SH sh,
                                               const v3 dL_dRGB, float* fact)
 {
 	v3 dir_orig = pos - campos;
@@ -166,7 +167,7 @@ __device__ __forceinline__ void cov3d_backward(const v3 scale, float mod, const 
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(PreprocessBwdArgs a)
+__global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(PreprocessBwdArgs a)
 {
 	extern __shared__ float4 s_dyn[]; // SH rows in, then basis factors out
 	__shared__ float s_cam[36];
@@ -220,10 +221,16 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(Preproc
 		__syncthreads();
 	}
 
-	float fact[16];
+	// basis factors + dL_dRGB of this Gaussian go straight to their own shared-memory row (not through
+	// registers); rows of Gaussians that do not run the SH chain must read as zero
+	float* const s_fact = reinterpret_cast<float*>(s_dyn) + a.fact_offset;
+	float* const fact = s_fact + threadIdx.x * FACT_PITCH;
+	const bool sh_rows = a.dL_dsh != nullptr && a.M > 0;
+	if (sh_rows && !(visible && a.shs != nullptr)) {
 #pragma unroll
-	for (int k = 0; k < 16; k++)
-		fact[k] = 0.f;
+		for (int k = 0; k < FACT_PITCH; k++)
+			fact[k] = 0.f;
+	}
 	v3 dL_dRGB = make_v3(0.f, 0.f, 0.f);
 
 	float3 o_mean2D = {0.f, 0.f, 0.f}, o_color = {0.f, 0.f, 0.f}, o_mean3D = {0.f, 0.f, 0.f};
@@ -362,16 +369,8 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(Preproc
 			v3 rgb;
 			float3 dmean_sh;
 			if (VEC) {
-				float c[48];
-				const float4* row = s_dyn + threadIdx.x * 13;
-#pragma unroll
-				for (int k = 0; k < 12; k++) {
-					const float4 v = row[k];
-					c[4 * k] = v.x;
-					c[4 * k + 1] = v.y;
-					c[4 * k + 2] = v.z;
-					c[4 * k + 3] = v.w;
-				}
+				// coefficients are read from the staged row where they are used (conflict-free LDS.128)
+				const ShRowView c{s_dyn + threadIdx.x * 13};
 				rgb = eval_sh(a.D, pos, cam, c);
 				dL_dRGB = make_v3(rgb.x < 0 ? 0.f : o_color.x, rgb.y < 0 ? 0.f : o_color.y, rgb.z < 0 ? 0.f : o_color.z);
 				dmean_sh = sh_backward(a.D, pos, cam, c, dL_dRGB, fact);
@@ -384,6 +383,11 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(Preproc
 			o_mean3D.x += dmean_sh.x;
 			o_mean3D.y += dmean_sh.y;
 			o_mean3D.z += dmean_sh.z;
+			if (sh_rows) {
+				fact[16] = dL_dRGB.x;
+				fact[17] = dL_dRGB.y;
+				fact[18] = dL_dRGB.z;
+			}
 		}
 
 		if (a.scales != nullptr)
@@ -439,17 +443,8 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(Preproc
 	}
 
 	// ---- dL_dsh rows: dL_dsh[k] = fact[k] * dL_dRGB, written coalesced through shared memory ----
-	if (a.dL_dsh != nullptr && a.M > 0) {
-		__syncthreads(); // everyone is done reading SH rows
-		float* s_fact = reinterpret_cast<float*>(s_dyn);
-		float* mine = s_fact + threadIdx.x * FACT_PITCH;
-#pragma unroll
-		for (int k = 0; k < 16; k++)
-			mine[k] = fact[k];
-		mine[16] = dL_dRGB.x;
-		mine[17] = dL_dRGB.y;
-		mine[18] = dL_dRGB.z;
-		__syncthreads();
+	if (sh_rows) {
+		__syncthreads(); // every row of s_fact is complete
 		const int rows = min(PB_THREADS, a.P - block_first);
 		if (VEC) {
 			float4* dst = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)block_first * 12;
@@ -506,18 +501,21 @@ cudaError_t launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t 
 	if (a.P <= 0)
 		return cudaSuccess;
 	const int blocks = (a.P + PB_THREADS - 1) / PB_THREADS;
-	size_t smem = (size_t)PB_THREADS * FACT_PITCH * sizeof(float);
+	// dynamic shared memory: [SH rows in | basis-factor rows out]
+	size_t in = 0;
 	bool vec = false;
 	if (a.shs != nullptr) {
 		vec = (a.M == 16) && ((reinterpret_cast<uintptr_t>(a.shs) & 15u) == 0) &&
 		      ((reinterpret_cast<uintptr_t>(a.dL_dsh) & 15u) == 0);
-		const size_t in = vec ? (size_t)PB_THREADS * 13 * sizeof(float4) : (size_t)PB_THREADS * ((3 * a.M) | 1) * sizeof(float);
-		smem = in > smem ? in : smem;
+		in = vec ? (size_t)PB_THREADS * 13 * sizeof(float4) : align_up((size_t)PB_THREADS * ((3 * a.M) | 1) * sizeof(float), 16);
 	}
+	PreprocessBwdArgs args = a;
+	args.fact_offset = (int)(in / sizeof(float));
+	const size_t smem = in + (size_t)PB_THREADS * FACT_PITCH * sizeof(float);
 	if (vec)
-		preprocess_backward_kernel<true><<<blocks, PB_THREADS, smem, stream>>>(a);
+		preprocess_backward_kernel<true><<<blocks, PB_THREADS, smem, stream>>>(args);
 	else
-		preprocess_backward_kernel<false><<<blocks, PB_THREADS, smem, stream>>>(a);
+		preprocess_backward_kernel<false><<<blocks, PB_THREADS, smem, stream>>>(args);
 	count_launch();
 	return cudaGetLastError();
 }

@@ -131,7 +131,7 @@ __device__ __forceinline__ bool compute_geometry(const float3 p_orig, const floa
 // minimum of q over its pixel block exceeds the value returned here: tau inflated by a bound on the
 // fp32 evaluation error of q (the reference's evaluation at the pixel AND the culling test's own at the
 // block's closest point) over every offset this Gaussian can meet (|d| <= radius + tile), plus an
-// absolute and a relative margin.  Computed in fp64 from the SAME fp32 conic the blend uses.
+// absolute and a relative margin.  Computed from the SAME fp32 conic the blend uses.
 // +inf (never cull) where no bound can be given, -inf (always cull) where opacity < 1/255 (alpha <= o).
 __device__ __forceinline__ float cull_tau(const float3 conic, float opacity, int radius)
 {
@@ -140,17 +140,18 @@ __device__ __forceinline__ float cull_tau(const float3 conic, float opacity, int
 		return -inf;
 	if (!(opacity <= 3.0e38f)) // NaN / inf opacity: let the blend decide
 		return inf;
-	const double a = conic.x, b = conic.y, c = conic.z;
-	const double det = a * c - b * b;
-	if (!(det > 0.0) || !(a > 0.0) || !(c > 0.0))
+	const float a = conic.x, b = conic.y, c = conic.z;
+	const float det = a * c - b * b;
+	if (!(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f))
 		return inf;
-	const double dmax = (double)radius + (double)(TILE_X + 1);
-	const double eval_err = 8.0 * 5.9604644775390625e-08 * (fabs(a) + fabs(c) + 2.0 * fabs(b)) * dmax * dmax;
-	double tau = 2.0 * log(255.0 * (double)opacity);
-	tau = (tau + 4.0 * eval_err + 1e-4) * (1.0 + 1e-5);
-	if (!(tau < 1e30))
+	const float dmax = (float)radius + (float)(TILE_X + 1);
+	const float eval_err = 8.0f * 5.9604644775390625e-08f * (fabsf(a) + fabsf(c) + 2.0f * fabsf(b)) * dmax * dmax;
+	// logf is good to a few ulp (~1e-6 absolute on a value of at most 11.1), far inside the 2e-4 margin
+	float tau = 2.0f * logf(255.0f * opacity);
+	tau = (tau + 4.0f * eval_err + 2e-4f) * (1.0f + 2e-5f);
+	if (!(tau < 1e30f))
 		return inf;
-	return (float)(tau * (1.0 + 1e-6) + 1e-6);
+	return tau;
 }
 
 // ---- K1 -----------------------------------------------------------------------------------------
@@ -241,18 +242,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 			const v3 cam = make_v3(s_cam[32], s_cam[33], s_cam[34]);
 			v3 res;
 			if (VEC) {
-				// 12 conflict-free LDS.128 into registers (constant indices below keep c[] in registers).
-				float c[48];
-				const float4* row = s_dyn + threadIdx.x * 13;
-#pragma unroll
-				for (int k = 0; k < 12; k++) {
-					const float4 v = row[k];
-					c[4 * k] = v.x;
-					c[4 * k + 1] = v.y;
-					c[4 * k + 2] = v.z;
-					c[4 * k + 3] = v.w;
-				}
-				res = eval_sh(a.D, pos, cam, c);
+				// coefficients are read from the staged row where they are used (conflict-free LDS.128)
+				res = eval_sh(a.D, pos, cam, ShRowView{s_dyn + threadIdx.x * 13});
 			} else {
 				res = eval_sh(a.D, pos, cam, reinterpret_cast<const float*>(s_dyn) + threadIdx.x * (row_f | 1));
 			}

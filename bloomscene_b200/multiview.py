@@ -40,6 +40,7 @@ class GaussianParams:
         self.grad_bucket = torch.zeros_like(self.flat)
         self.tensors: Dict[str, torch.Tensor] = {}
         self._lanes: List = []
+        self._zero_means2D = None
         off = 0
         for n, sz in zip(self.names, sizes):
             seg = self.flat[off:off + sz].view(tensors[n].shape)
@@ -57,6 +58,13 @@ class GaussianParams:
         self.grad_bucket.zero_()
         for b, _ in self._lanes:
             b.zero_()
+
+    def zero_means2D(self) -> torch.Tensor:
+        """The all-zero `means2D` input every view passes in (reference gaussian_renderer/__init__.py:224-229
+        creates a fresh zeros_like per call); it is only a gradient carrier, so one buffer serves all views."""
+        if self._zero_means2D is None:
+            self._zero_means2D = torch.zeros_like(self.tensors["means3D"].detach())
+        return self._zero_means2D
 
     def lane_sinks(self, n: int) -> List[Dict[str, torch.Tensor]]:
         """`n` gradient sinks with the layout of `grads()`: the bucket itself plus n-1 private buckets, one
@@ -120,7 +128,7 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
         settings = raster_settings(cam, params.sh_degree, bg, GaussianRasterizationSettings)
         sink = sinks[lane]
         rast = rasterizer_cls(settings, grad_sink=sink) if sink is not None else rasterizer_cls(raster_settings=settings)
-        means2D = torch.zeros_like(params.tensors["means3D"], requires_grad=True)
+        means2D = params.zero_means2D().detach().requires_grad_(True)  # fresh leaf over a shared zero buffer
         color, radii, depth = rast(means3D=params.tensors["means3D"], means2D=means2D,
                                    opacities=params.tensors["opacities"], shs=params.get("shs"),
                                    colors_precomp=params.get("colors_precomp"), scales=params.tensors["scales"],

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 	for (int base = 0, buf = 0; base < n; base += BATCH, buf ^= 1) {
 		cp_async_wait_all();
 		bool warp_done = __all_sync(0xffffffffu, done);
+		(void)warp_done;
 		// one barrier per batch: buffer `buf` is complete and visible, buffer `buf ^ 1` is no longer read
 		if (__syncthreads_and(warp_done))
 			break;
@@ -68,12 +69,17 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 
 		const StagedRecord* rec = s_rec[buf];
 		const int cnt = min(BATCH, n - base);
-		for (int c0 = 0; c0 < cnt && !warp_done; c0 += 32) {
+		for (int c0 = 0; c0 < cnt; c0 += 32) {
+			// a warp leaves as soon as all of its 32 pixels have saturated (checked once per chunk: after the
+			// exact culling ~97 % of the evaluated records contribute, so a per-record vote does not pay)
+			if (__all_sync(0xffffffffu, done)) {
+				warp_done = true;
+				break;
+			}
 			const int e = c0 + (int)lane;
 			bool hit = false;
-			if (e < cnt) {
+			if (e < cnt)
 				hit = block_may_contribute(rec[e].geo, rec[e].con, wx0, wx1, wy0, wy1);
-			}
 			uint32_t mask = __ballot_sync(0xffffffffu, hit);
 			while (mask) {
 				const int j = __ffs(mask) - 1;
@@ -81,6 +87,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 				const StagedRecord* r = rec + (c0 + j);
 				const float2 gxy = *reinterpret_cast<const float2*>(&r->geo);
 				const float4 con = r->con;
+				const float4 col = r->col;
 				const float dx = gxy.x - pixfx;
 				const float dy = gxy.y - pixfy;
 				const float t1 = __fmul_rn(dy, __fmul_rn(dy, con.z));
@@ -94,20 +101,14 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 					done = true;
 					ok = false;
 				}
-				if (__any_sync(0xffffffffu, ok)) {
-					const float4 col = r->col;
-					if (ok) {
-						C0 = __fmaf_rn(T, __fmul_rn(alpha, col.x), C0);
-						C1 = __fmaf_rn(T, __fmul_rn(alpha, col.y), C1);
-						C2 = __fmaf_rn(T, __fmul_rn(alpha, col.z), C2);
-						D = __fmaf_rn(T, __fmul_rn(alpha, col.w), D);
-						acc = __fmaf_rn(T, alpha, acc);
-						T = test_T;
-						last_contributor = (uint32_t)(base + c0 + j + 1);
-					}
-				} else if (__all_sync(0xffffffffu, done)) {
-					warp_done = true;
-					break;
+				if (ok) {
+					C0 = __fmaf_rn(T, __fmul_rn(alpha, col.x), C0);
+					C1 = __fmaf_rn(T, __fmul_rn(alpha, col.y), C1);
+					C2 = __fmaf_rn(T, __fmul_rn(alpha, col.z), C2);
+					D = __fmaf_rn(T, __fmul_rn(alpha, col.w), D);
+					acc = __fmaf_rn(T, alpha, acc);
+					T = test_T;
+					last_contributor = (uint32_t)(base + c0 + j + 1);
 				}
 			}
 		}

@@ -222,7 +222,10 @@ def main():
     bg = torch.zeros(3, device=dev)
     params = GaussianParams(scene)
     del scene
-    loss_fn = lambda color, depth, vi: (color * Wc).sum() + (depth * Wd).sum()
+    # loss = <color, Wc> + <depth, Wd>, written as two dot products: one reduction kernel
+    # forward and one scaling kernel backward per term, for both arms alike
+    Wc_flat, Wd_flat = Wc.reshape(-1), Wd.reshape(-1)
+    loss_fn = lambda color, depth, vi: torch.dot(color.reshape(-1), Wc_flat) + torch.dot(depth.reshape(-1), Wd_flat)
 
     # pinned host mirrors for the end-to-end leg
     host_params = torch.empty_like(params.flat, device="cpu").pin_memory()

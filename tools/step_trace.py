@@ -34,7 +34,10 @@ def main():
     Wc, Wd = [t.to(dev) for t in synthetic.loss_weights(cfg["W"], cfg["H"])]
     bg = torch.zeros(3, device=dev)
     params = GaussianParams(scene)
-    loss_fn = lambda color, depth, vi: (color * Wc).sum() + (depth * Wd).sum()
+    # loss = <color, Wc> + <depth, Wd>, written as two dot products: one reduction kernel
+    # forward and one scaling kernel backward per term, for both arms alike
+    Wc_flat, Wd_flat = Wc.reshape(-1), Wd.reshape(-1)
+    loss_fn = lambda color, depth, vi: torch.dot(color.reshape(-1), Wc_flat) + torch.dot(depth.reshape(-1), Wd_flat)
     step = lambda: view_sharded_step(params, cams, bg, api.GaussianRasterizer, loss_fn)
     for _ in range(2):
         step()

@@ -9,9 +9,11 @@
 //     caller needs no zero-fill: the reference zero-fills (108 + 12 M) bytes per Gaussian first
 //     (rasterize_points.cu:154-162);
 //   * or, in ACCUMULATE mode (brs_grads.accumulate, used by the view-sharded step), adds the parameter
-//     gradients of the visible Gaussians straight into the caller's gradient bucket, which replaces
-//     one fresh (44 + 12 M)-byte-per-Gaussian tensor set plus a read-modify-write pass over the
-//     bucket per view by a single read-modify-write of the visible rows;
+//     gradients of the visible Gaussians straight into the caller's gradient bucket with float
+//     reductions (red.global.add, 16-byte vectors for the SH rows), which replaces one fresh
+//     (44 + 12 M)-byte-per-Gaussian tensor set plus a read-modify-write pass over the bucket per view
+//     by a single reduction of the visible rows — and is safe when views on different streams add
+//     into the same bucket concurrently;
 //   * recomputes cov3D and the SH colour sign (`clamped`) with the forward's device functions
 //     instead of reading stored copies;
 //   * stages SH rows (in) and dL_dsh rows (out) through shared memory so that global traffic is
@@ -25,6 +27,13 @@ namespace brs {
 namespace {
 
 constexpr int PB_THREADS = 128;
+
+// 16-byte vector reduction (sm_90+): four float adds in one L2 atomic, no return value.
+__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w)
+{
+	asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w)
+	             : "memory");
+}
 constexpr int FACT_PITCH = 19; // 16 basis factors + dL_dRGB, odd pitch -> conflict-free
 
 // reference auxiliary.h:107-117
@@ -417,28 +426,39 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 			p = a.dL_drotations + 4 * (size_t)idx;
 			p[0] = o_rot.x; p[1] = o_rot.y; p[2] = o_rot.z; p[3] = o_rot.w;
 		} else if (visible) {
-			float* pm = a.dL_dmeans3D + 3 * (size_t)idx;
-			float* po = a.dL_dopacity + idx;
-			const float m0 = pm[0], m1 = pm[1], m2 = pm[2], op = po[0];
+			// float atomics (RED, no return value): several views may be adding into the same bucket from
+			// different streams at the same time
+			float* p3 = a.dL_dmeans3D + 3 * (size_t)idx;
+			atomicAdd(p3 + 0, o_mean3D.x);
+			atomicAdd(p3 + 1, o_mean3D.y);
+			atomicAdd(p3 + 2, o_mean3D.z);
+			atomicAdd(a.dL_dopacity + idx, o_opacity);
 			if (a.scales != nullptr) {
 				float* ps = a.dL_dscales + 3 * (size_t)idx;
+				atomicAdd(ps + 0, o_scale.x);
+				atomicAdd(ps + 1, o_scale.y);
+				atomicAdd(ps + 2, o_scale.z);
 				float* pr = a.dL_drotations + 4 * (size_t)idx;
-				const float s0 = ps[0], s1 = ps[1], s2 = ps[2];
-				const float r0 = pr[0], r1 = pr[1], r2 = pr[2], r3 = pr[3];
-				ps[0] = s0 + o_scale.x; ps[1] = s1 + o_scale.y; ps[2] = s2 + o_scale.z;
-				pr[0] = r0 + o_rot.x; pr[1] = r1 + o_rot.y; pr[2] = r2 + o_rot.z; pr[3] = r3 + o_rot.w;
+				if ((reinterpret_cast<uintptr_t>(a.dL_drotations) & 15u) == 0) {
+					red_add_v4(pr, o_rot.x, o_rot.y, o_rot.z, o_rot.w);
+				} else { // a bucket slice that is not 16-byte aligned (odd P)
+					atomicAdd(pr + 0, o_rot.x);
+					atomicAdd(pr + 1, o_rot.y);
+					atomicAdd(pr + 2, o_rot.z);
+					atomicAdd(pr + 3, o_rot.w);
+				}
 			} else {
 				p = a.dL_dcov3D + 6 * (size_t)idx;
 #pragma unroll
 				for (int i = 0; i < 6; i++)
-					p[i] += o_cov[i];
+					atomicAdd(p + i, o_cov[i]);
 			}
 			if (a.shs == nullptr) {
 				p = a.dL_dcolors + 3 * (size_t)idx;
-				p[0] += o_color.x; p[1] += o_color.y; p[2] += o_color.z;
+				atomicAdd(p + 0, o_color.x);
+				atomicAdd(p + 1, o_color.y);
+				atomicAdd(p + 2, o_color.z);
 			}
-			pm[0] = m0 + o_mean3D.x; pm[1] = m1 + o_mean3D.y; pm[2] = m2 + o_mean3D.z;
-			po[0] = op + o_opacity;
 		}
 	}
 
@@ -448,18 +468,6 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 		const int rows = min(PB_THREADS, a.P - block_first);
 		if (VEC) {
 			float4* dst = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)block_first * 12;
-			float4 old[12];
-			if (a.accumulate) {
-				// all loads first (memory-level parallelism), rows of culled Gaussians are skipped
-#pragma unroll
-				for (int k = 0; k < 12; k++) {
-					const int f = threadIdx.x + PB_THREADS * k;
-					const int row = f / 12;
-					old[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-					if (row < rows && ((s_vis[row >> 5] >> (row & 31)) & 1u))
-						old[k] = dst[f];
-				}
-			}
 #pragma unroll
 			for (int k = 0; k < 12; k++) {
 				const int f = threadIdx.x + PB_THREADS * k;
@@ -473,7 +481,7 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 						o[q] = fr[e / 3] * fr[16 + (e % 3)];
 					}
 					if (a.accumulate)
-						dst[f] = make_float4(old[k].x + o[0], old[k].y + o[1], old[k].z + o[2], old[k].w + o[3]);
+						red_add_v4(reinterpret_cast<float*>(dst + f), o[0], o[1], o[2], o[3]);
 					else
 						dst[f] = make_float4(o[0], o[1], o[2], o[3]);
 				}
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 				if (!a.accumulate)
 					dst[f] = val;
 				else if ((s_vis[row >> 5] >> (row & 31)) & 1u)
-					dst[f] += val;
+					atomicAdd(dst + f, val);
 			}
 		}
 	}

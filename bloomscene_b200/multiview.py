@@ -27,8 +27,9 @@ class GaussianParams:
     """Gaussian parameters packed in one flat fp32 buffer with a matching flat gradient bucket.
 
     Each parameter tensor is a leaf view into `flat`, and its `.grad` is preset to the matching view
-    of `grad_bucket`, so autograd accumulates every view's gradients straight into the bucket and a
-    single allreduce covers all parameters ((44 + 12 M) bytes per Gaussian)."""
+    of `grad_bucket`, so every view's gradients land straight in the bucket (added by the kernel itself
+    with the native rasterizer, by autograd otherwise) and a single allreduce covers all parameters
+    ((44 + 12 M) bytes per Gaussian)."""
 
     def __init__(self, scene: Scene):
         tensors = {k: v for k, v in scene.tensors().items()}
@@ -39,7 +40,6 @@ class GaussianParams:
         self.flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         self.grad_bucket = torch.zeros_like(self.flat)
         self.tensors: Dict[str, torch.Tensor] = {}
-        self._lanes: List = []
         self._zero_means2D = None
         off = 0
         for n, sz in zip(self.names, sizes):
@@ -56,8 +56,6 @@ class GaussianParams:
 
     def zero_grad(self):
         self.grad_bucket.zero_()
-        for b, _ in self._lanes:
-            b.zero_()
 
     def zero_means2D(self) -> torch.Tensor:
         """The all-zero `means2D` input every view passes in (reference gaussian_renderer/__init__.py:224-229
@@ -65,23 +63,6 @@ class GaussianParams:
         if self._zero_means2D is None:
             self._zero_means2D = torch.zeros_like(self.tensors["means3D"].detach())
         return self._zero_means2D
-
-    def lane_sinks(self, n: int) -> List[Dict[str, torch.Tensor]]:
-        """`n` gradient sinks with the layout of `grads()`: the bucket itself plus n-1 private buckets, one
-        per concurrent stream of the step (two kernels adding into one bucket at the same time would race)."""
-        while len(self._lanes) < n - 1:
-            b = torch.zeros_like(self.grad_bucket)
-            views, off = {}, 0
-            for name in self.names:
-                t = self.tensors[name]
-                views[name] = b[off:off + t.numel()].view(t.shape)
-                off += t.numel()
-            self._lanes.append((b, views))
-        return [self.grads()] + [v for _, v in self._lanes[:n - 1]]
-
-    def fold_lanes(self, n: int):
-        for b, _ in self._lanes[:n - 1]:
-            self.grad_bucket.add_(b)
 
     def grads(self) -> Dict[str, torch.Tensor]:
         return {n: t.grad for n, t in self.tensors.items()}
@@ -110,8 +91,8 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
     With the native rasterizer on a GPU the views are dealt round-robin onto `streams` CUDA streams: a
     view's preprocess / sort / binning kernels (small grids, latency- and bandwidth-bound) then run
     under another view's blend kernels (issue-bound), and the forward's one host wait for a view falls
-    while the other stream still has a backward queued.  Each stream adds into its own gradient bucket
-    (folded into the main one before the allreduce)."""
+    while the other stream still has a backward queued.  All streams add into the one gradient bucket:
+    the kernel accumulates with float reductions (brs_grads.accumulate)."""
     params.zero_grad()
     mine = shard_views(len(cameras), rank, world)
     dev = params.flat.device
@@ -120,13 +101,12 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
     # any other rasterizer (the reference build, the CPU stand-in of the tests) goes through autograd
     use_sink = getattr(rasterizer_cls, "supports_grad_sink", False)
     n_lanes = max(1, min(streams, len(mine))) if (use_sink and dev.type == "cuda") else 1
-    sinks = params.lane_sinks(n_lanes) if use_sink else [None]
+    sink = params.grads() if use_sink else None
     losses = [torch.zeros((), dtype=torch.float32, device=dev) for _ in range(n_lanes)]
 
     def one_view(vi: int, lane: int):
         cam = cameras[vi]
         settings = raster_settings(cam, params.sh_degree, bg, GaussianRasterizationSettings)
-        sink = sinks[lane]
         rast = rasterizer_cls(settings, grad_sink=sink) if sink is not None else rasterizer_cls(raster_settings=settings)
         means2D = params.zero_means2D().detach().requires_grad_(True)  # fresh leaf over a shared zero buffer
         color, radii, depth = rast(means3D=params.tensors["means3D"], means2D=means2D,
@@ -145,13 +125,12 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
         cur = torch.cuda.current_stream(dev)
         lanes = _lane_streams(dev, n_lanes)
         for st in lanes:
-            st.wait_stream(cur)  # parameters, zeroed buckets
+            st.wait_stream(cur)  # parameters, zeroed bucket
         for j, vi in enumerate(mine):
             with torch.cuda.stream(lanes[j % n_lanes]):
                 one_view(vi, j % n_lanes)
         for st in lanes:
             cur.wait_stream(st)
-        params.fold_lanes(n_lanes)
     loss_sum = losses[0]
     for extra in losses[1:]:
         loss_sum = loss_sum + extra

@@ -25,7 +25,7 @@
 // Traffic is ~70 P + 16 R1 + 4 R bytes instead of the reference's 152 R.
 //
 // The radix sort is hand-written.  Each pass over one digit is three kernels:
-//   upsweep   : per 4096-key tile, digit counts (warp match_any + shared atomics)  -> table[digit][tile]
+//   upsweep   : per 2048-key tile, digit counts (warp match_any + shared atomics)  -> table[digit][tile]
 //   scan      : one block per digit, exclusive scan along the tiles + digit totals
 //   downsweep : per tile, stable ranks (match_any + shared atomics returning the old value, so the
 //               16 keys of a thread are in flight together), scatter through shared memory so
@@ -42,8 +42,8 @@ namespace {
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 pairs per tile
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 2048 pairs per tile (smaller tiles = more CTAs in flight: the passes are latency-bound chains of MATCH/ATOMS)
 constexpr int RADIX_MAX = 256;
 constexpr int MAX_PASSES = 4;
 

@@ -211,7 +211,7 @@ def main():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/_ref_C.so is not built (needs /root/reference at build time)"}))
         return
 
-    from bloomscene_b200.multiview import GaussianParams, view_sharded_step
+    from bloomscene_b200.multiview import GaussianParams, download_grads, upload_params, view_sharded_step
 
     scene_cpu = synthetic.config_scene(CONFIG_NAME)
     cams_cpu = synthetic.config_cameras(CONFIG_NAME, a.views)
@@ -246,12 +246,16 @@ def main():
         return view_sharded_step(params, cams, bg, api.GaussianRasterizer, loss_fn, rank=rank_eff, world=world_eff,
                                  streams=a.streams)
 
+    moved = {"h2d": 0, "d2h": 0}
+
     def step_e2e():
+        # every rank moves its 1/N slice of the parameters / gradients over its own PCIe link; the slices
+        # travel between GPUs over NVLink (all-gather in upload_params, the step's allreduce before download)
+        moved["h2d"] = upload_params(params, host_params, rank_eff, world_eff) + cam_host.numel() * 4
         with torch.no_grad():
-            params.flat.copy_(host_params, non_blocking=True)
             cam_dev.copy_(cam_host, non_blocking=True)
         res = step()
-        host_grads.copy_(params.grad_bucket, non_blocking=True)
+        moved["d2h"] = download_grads(params, host_grads, rank_eff, world_eff) + 4
         host_loss.copy_(res["loss"].reshape(1), non_blocking=True)
         return res
 
@@ -293,8 +297,14 @@ def main():
         dist.all_reduce(t)
         launches = int(t.item())
 
-    h2d = host_params.numel() * 4 + cam_host.numel() * 4
-    d2h = host_grads.numel() * 4 + 4
+    # whole-job host traffic per step = sum over ranks of what each rank copied
+    h2d, d2h = moved["h2d"], moved["d2h"]
+    if world_eff > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
     out = {
         "metric": METRIC, "value": a.views / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world_eff, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms_step, "ms_per_view": ms_step / a.views,
@@ -303,7 +313,9 @@ def main():
         "e2e": {"value": a.views / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e,
                 "what": "per step: all Gaussian parameters + cameras pinned host->device, then the view loop through "
-                        "GaussianRasterizer / autograd, then gradient bucket + loss device->pinned host"},
+                        "GaussianRasterizer / autograd, then gradient bucket + loss device->pinned host; with N ranks "
+                        "each rank copies its 1/N slice of the parameters / the reduced gradients over its own PCIe "
+                        "link (slices exchanged over NVLink), bytes are whole-job totals"},
         "loss": loss_value,
     }
     if a.impl == "reference":

@@ -175,7 +175,6 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 {
 	extern __shared__ float4 s_dyn[]; // SH staging (only when a.shs != nullptr)
 	__shared__ float s_cam[36];
-	__shared__ uint32_t s_vis[PRE_THREADS / 32];
 	__shared__ uint32_t s_tiles[5][PRE_THREADS / 32];
 
 	stage_camera(s_cam, a.viewmatrix, a.projmatrix, a.campos);
@@ -209,34 +208,33 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	// ---- colour ----
 	float3 rgb = {0.f, 0.f, 0.f};
 	if (a.shs != nullptr) {
-		if (lane == 0)
-			s_vis[warp] = vis_mask;
-		__syncthreads();
+		// every warp stages the rows of ITS 32 Gaussians (no block barrier: warps of a block overlap
+		// their geometry, load and evaluation phases)
 		const int row_f = 3 * a.M; // floats per Gaussian
+		const int warp_first = block_first + 32 * warp;
 		if (VEC) {
 			// 12 float4 per row, pitch 13 float4: lane-consecutive LDS.128 rows are conflict-free.
-			const float4* src = reinterpret_cast<const float4*>(a.shs) + (size_t)block_first * 12;
+			const float4* src = reinterpret_cast<const float4*>(a.shs) + (size_t)warp_first * 12;
+			float4* dst = s_dyn + 32 * warp * 13;
 #pragma unroll
 			for (int k = 0; k < 12; k++) {
-				const int f = threadIdx.x + PRE_THREADS * k;
+				const int f = lane + 32 * k;
 				const int row = f / 12, col = f - row * 12;
-				const bool want = (s_vis[row >> 5] >> (row & 31)) & 1u;
-				if (want)
-					s_dyn[row * 13 + col] = ldg_stream_f4(src + f);
+				if ((vis_mask >> row) & 1u)
+					dst[row * 13 + col] = ldg_stream_f4(src + f);
 			}
 		} else {
-			float* s_sh = reinterpret_cast<float*>(s_dyn);
 			const int pitch = row_f | 1; // odd pitch: conflict-free scalar reads
-			const float* src = a.shs + (size_t)block_first * row_f;
-			const int total = PRE_THREADS * row_f;
-			for (int f = threadIdx.x; f < total; f += PRE_THREADS) {
+			float* s_sh = reinterpret_cast<float*>(s_dyn) + 32 * warp * pitch;
+			const float* src = a.shs + (size_t)warp_first * row_f;
+			const int total = 32 * row_f;
+			for (int f = lane; f < total; f += 32) {
 				const int row = f / row_f, col = f - row * row_f;
-				const bool want = (s_vis[row >> 5] >> (row & 31)) & 1u;
-				if (want)
+				if ((vis_mask >> row) & 1u)
 					s_sh[row * pitch + col] = __ldg(src + f);
 			}
 		}
-		__syncthreads();
+		__syncwarp();
 		if (visible) {
 			const v3 pos = make_v3(p_orig.x, p_orig.y, p_orig.z);
 			const v3 cam = make_v3(s_cam[32], s_cam[33], s_cam[34]);

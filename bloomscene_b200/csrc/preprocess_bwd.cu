@@ -180,7 +180,6 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 {
 	extern __shared__ float4 s_dyn[]; // SH rows in, then basis factors out
 	__shared__ float s_cam[36];
-	__shared__ uint32_t s_vis[PB_THREADS / 32];
 
 	{
 		const int t = threadIdx.x;
@@ -198,36 +197,36 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 	const bool in_range = idx < a.P;
 	const bool visible = in_range && (__ldg(a.radii + idx) > 0);
 	const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
-	if (lane == 0)
-		s_vis[warp] = vis_mask;
-	__syncthreads();
+	__syncthreads(); // camera block
 	const float* view = s_cam;
 	const float* proj = s_cam + 16;
 
 	const int row_f = 3 * a.M;
-	// ---- stage SH rows of visible Gaussians ----
+	const int warp_first = block_first + 32 * warp;
+	// ---- every warp stages the SH rows of ITS visible Gaussians (no block barrier between the phases) ----
 	if (a.shs != nullptr) {
 		if (VEC) {
-			const float4* src = reinterpret_cast<const float4*>(a.shs) + (size_t)block_first * 12;
+			const float4* src = reinterpret_cast<const float4*>(a.shs) + (size_t)warp_first * 12;
+			float4* dst = s_dyn + 32 * warp * 13;
 #pragma unroll
 			for (int k = 0; k < 12; k++) {
-				const int f = threadIdx.x + PB_THREADS * k;
+				const int f = lane + 32 * k;
 				const int row = f / 12, col = f - row * 12;
-				if ((s_vis[row >> 5] >> (row & 31)) & 1u)
-					s_dyn[row * 13 + col] = ldg_stream_f4(src + f);
+				if ((vis_mask >> row) & 1u)
+					dst[row * 13 + col] = ldg_stream_f4(src + f);
 			}
 		} else {
-			float* s_sh = reinterpret_cast<float*>(s_dyn);
 			const int pitch = row_f | 1;
-			const float* src = a.shs + (size_t)block_first * row_f;
-			const int total = PB_THREADS * row_f;
-			for (int f = threadIdx.x; f < total; f += PB_THREADS) {
+			float* s_sh = reinterpret_cast<float*>(s_dyn) + 32 * warp * pitch;
+			const float* src = a.shs + (size_t)warp_first * row_f;
+			const int total = 32 * row_f;
+			for (int f = lane; f < total; f += 32) {
 				const int row = f / row_f, col = f - row * row_f;
-				if ((s_vis[row >> 5] >> (row & 31)) & 1u)
+				if ((vis_mask >> row) & 1u)
 					s_sh[row * pitch + col] = __ldg(src + f);
 			}
 		}
-		__syncthreads();
+		__syncwarp();
 	}
 
 	// basis factors + dL_dRGB of this Gaussian go straight to their own shared-memory row (not through
@@ -464,16 +463,17 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 
 	// ---- dL_dsh rows: dL_dsh[k] = fact[k] * dL_dRGB, written coalesced through shared memory ----
 	if (sh_rows) {
-		__syncthreads(); // every row of s_fact is complete
-		const int rows = min(PB_THREADS, a.P - block_first);
+		__syncwarp(); // the 32 rows of this warp in s_fact are complete
+		const int rows = min(32, a.P - warp_first);
+		const float* wfact = s_fact + 32 * warp * FACT_PITCH;
 		if (VEC) {
-			float4* dst = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)block_first * 12;
+			float4* dst = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)warp_first * 12;
 #pragma unroll
 			for (int k = 0; k < 12; k++) {
-				const int f = threadIdx.x + PB_THREADS * k;
+				const int f = lane + 32 * k;
 				const int row = f / 12, col = f - row * 12;
-				if (row < rows && (!a.accumulate || ((s_vis[row >> 5] >> (row & 31)) & 1u))) {
-					const float* fr = s_fact + row * FACT_PITCH;
+				if (row < rows && (!a.accumulate || ((vis_mask >> row) & 1u))) {
+					const float* fr = wfact + row * FACT_PITCH;
 					float o[4];
 #pragma unroll
 					for (int q = 0; q < 4; q++) {
@@ -487,15 +487,15 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 				}
 			}
 		} else {
-			float* dst = a.dL_dsh + (size_t)block_first * row_f;
+			float* dst = a.dL_dsh + (size_t)warp_first * row_f;
 			const int total = rows * row_f;
-			for (int f = threadIdx.x; f < total; f += PB_THREADS) {
+			for (int f = lane; f < total; f += 32) {
 				const int row = f / row_f, e = f - row * row_f;
-				const float* fr = s_fact + row * FACT_PITCH;
+				const float* fr = wfact + row * FACT_PITCH;
 				const float val = fr[e / 3] * fr[16 + (e % 3)];
 				if (!a.accumulate)
 					dst[f] = val;
-				else if ((s_vis[row >> 5] >> (row & 31)) & 1u)
+				else if ((vis_mask >> row) & 1u)
 					atomicAdd(dst + f, val);
 			}
 		}

@@ -142,6 +142,47 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
     return {"loss": loss_sum, "views": mine, "radii": visible}
 
 
+def _slice_bounds(numel: int, rank: int, world: int):
+    """Contiguous 1/world slice of a flat buffer owned by `rank` (last slice takes the remainder)."""
+    per = (numel + world - 1) // world
+    lo = min(numel, rank * per)
+    return lo, min(numel, lo + per)
+
+
+def upload_params(params: GaussianParams, host_flat: torch.Tensor, rank: int = 0, world: int = 1, group=None) -> int:
+    """Host -> device refresh of the replicated parameter buffer for steps whose parameters live on the
+    host (e.g. a host-side optimizer).  With N ranks every rank copies only ITS 1/N slice over its own
+    PCIe link and the slices are exchanged over NVLink (all-gather), so the host traffic of the whole
+    job is one copy of the parameters instead of N.  Returns the bytes this rank copied from the host."""
+    n = params.flat.numel()
+    with torch.no_grad():
+        if world == 1:
+            params.flat.copy_(host_flat, non_blocking=True)
+            return n * 4
+        import torch.distributed as dist
+
+        lo, hi = _slice_bounds(n, rank, world)
+        params.flat[lo:hi].copy_(host_flat[lo:hi], non_blocking=True)
+        if n % world == 0:
+            mine = params.flat[lo:hi]  # NCCL gathers in place (input = this rank's slot of the output)
+            dist.all_gather_into_tensor(params.flat, mine if mine.is_cuda else mine.clone(), group=group)
+        else:
+            for r in range(world):
+                a, b = _slice_bounds(n, r, world)
+                if b > a:
+                    dist.broadcast(params.flat[a:b], src=r, group=group)
+        return (hi - lo) * 4
+
+
+def download_grads(params: GaussianParams, host_grads: torch.Tensor, rank: int = 0, world: int = 1) -> int:
+    """Device -> host copy of the (already all-reduced) gradient bucket: rank r writes slice r of the
+    host buffer, so the N ranks of a node fill one host gradient with N parallel PCIe copies.
+    Returns the bytes this rank copied."""
+    lo, hi = _slice_bounds(params.grad_bucket.numel(), rank, world)
+    host_grads[lo:hi].copy_(params.grad_bucket[lo:hi], non_blocking=True)
+    return (hi - lo) * 4
+
+
 _LANE_STREAMS: Dict[object, list] = {}
 
 

@@ -49,7 +49,27 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     api, params, cams, loss_fn = _setup()
     res = view_sharded_step(params, cams, torch.zeros(3), api.GaussianRasterizer, loss_fn, rank=rank, world=world)
-    torch.save({"bucket": params.grad_bucket.clone(), "loss": res["loss"], "views": res["views"]},
+    # sharded host staging: every rank uploads / downloads only its slice, the rest travels rank to rank
+    from bloomscene_b200.multiview import download_grads, upload_params
+
+    host_grads = torch.zeros_like(params.grad_bucket)
+    down = download_grads(params, host_grads, rank, world)
+    staged = {}
+    for trim in (0, 1):  # numel divisible by the world size (all-gather) and not (per-slice broadcasts)
+        n = params.flat.numel() - trim
+        host_params = torch.arange(params.flat.numel(), dtype=torch.float32) * 0.5 + 1.0
+        saved = params.flat.detach().clone()
+        if trim:
+            class _Trim:  # a parameter set whose flat buffer is one element shorter
+                flat = params.flat.detach()[:n]
+            up = upload_params(_Trim, host_params[:n], rank, world)
+        else:
+            up = upload_params(params, host_params, rank, world)
+        staged[trim] = (up, torch.equal(params.flat.detach()[:n], host_params[:n]))
+        with torch.no_grad():
+            params.flat.copy_(saved)
+    torch.save({"bucket": params.grad_bucket.clone(), "loss": res["loss"], "views": res["views"],
+                "host_grads": host_grads, "down": down, "staged": staged},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -77,3 +97,11 @@ def test_view_sharded_step_matches_single_process(tmp_path):
     rel = (r0["bucket"].double() - ref_bucket.double()).norm() / ref_bucket.double().norm()
     assert rel <= 1e-5
     assert abs(r0["loss"].item() - single["loss"].item()) <= 1e-4 * abs(single["loss"].item())
+    # host staging: the two ranks' downloads tile the reduced bucket, uploads reproduce the host copy everywhere
+    n = ref_bucket.numel()
+    assert r0["down"] + r1["down"] == 4 * n
+    assert torch.equal(r0["host_grads"] + r1["host_grads"], r0["bucket"])
+    for r in (r0, r1):
+        for trim in (0, 1):
+            up, same = r["staged"][trim]
+            assert same and up < 4 * n

@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--cpu-views", type=int, default=3, help="views of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a rank are dealt onto (ours only)")
+    ap.add_argument("--host-threads", type=int, default=0, help="1: one host thread per stream (ours only)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "cpu" else a.warmup
 
@@ -244,7 +245,7 @@ def main():
 
     def step():
         return view_sharded_step(params, cams, bg, api.GaussianRasterizer, loss_fn, rank=rank_eff, world=world_eff,
-                                 streams=a.streams)
+                                 streams=a.streams, host_threads=bool(a.host_threads))
 
     moved = {"h2d": 0, "d2h": 0}
 

@@ -36,11 +36,13 @@ _api = bind(_C)
 GaussianRasterizer = _api.GaussianRasterizer
 rasterize_gaussians = _api.rasterize_gaussians
 _RasterizeGaussians = _api._RasterizeGaussians
+render_views = _api.render_views
 
 __all__ = [
     "GaussianRasterizationSettings",
     "GaussianRasterizer",
     "rasterize_gaussians",
+    "render_views",
     "_RasterizeGaussians",
     "cpu_deep_copy_tuple",
     "bind",

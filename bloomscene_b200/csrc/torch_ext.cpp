@@ -465,9 +465,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("stage_timing", [](bool enable) { brs_stage_timing(enable ? 1 : 0); });
 	m.def("stage_times", &StageTimes);
 	m.def("probe_fp32_tflops", []() { return brs_probe_fp32_tflops(current_stream()); });
-	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
-	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
-	m.def("rasterize_gaussians_backward_accumulate", &RasterizeGaussiansBackwardAccumulateCUDA);
+	// the forward blocks once on the device (instance count); it touches no Python object, so it runs
+	// without the GIL and several host threads can drive one CUDA stream each (render_views)
+	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
+	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
+	m.def("rasterize_gaussians_backward_accumulate", &RasterizeGaussiansBackwardAccumulateCUDA,
+	      pybind11::call_guard<pybind11::gil_scoped_release>());
 	m.def("rasterize_aussians_filter", &RasterizeGaussiansfilterCUDA);
 	m.def("mark_visible", &markVisible);
 	m.def("sort_pairs", &SortPairs, pybind11::arg("keys"), pybind11::arg("vals") = pybind11::none(),

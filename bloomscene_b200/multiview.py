@@ -13,11 +13,12 @@ logic can be tested on CPU with an oracle-backed stand-in (tests only).
 """
 from __future__ import annotations
 
+from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings
+from .rasterizer import GaussianRasterizationSettings, lane_streams
 from .synthetic import Camera, Scene, raster_settings
 
 _ORDER = ("means3D", "scales", "rotations", "opacities", "shs", "colors_precomp")
@@ -83,7 +84,7 @@ def default_loss(color: torch.Tensor, depth: torch.Tensor, Wc: torch.Tensor, Wd:
 def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: torch.Tensor, rasterizer_cls,
                       loss_fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor],
                       rank: int = 0, world: int = 1, group=None, allreduce: bool = True,
-                      streams: int = 4) -> Dict[str, object]:
+                      streams: int = 4, host_threads: bool = False) -> Dict[str, object]:
     """Render this rank's slice of `cameras`, backpropagate `loss_fn(color, depth, view_index)`, sum the
     parameter gradients over ranks.  Returns the step loss (summed over all views), per-view radii
     counts and the number of views rendered locally.
@@ -123,12 +124,24 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
             one_view(vi, 0)
     else:
         cur = torch.cuda.current_stream(dev)
-        lanes = _lane_streams(dev, n_lanes)
+        lanes = lane_streams(dev, n_lanes)
         for st in lanes:
             st.wait_stream(cur)  # parameters, zeroed bucket
-        for j, vi in enumerate(mine):
-            with torch.cuda.stream(lanes[j % n_lanes]):
-                one_view(vi, j % n_lanes)
+        if host_threads:
+            # one host thread per stream: the native calls release the GIL, so one view's host wait and
+            # kernel launches do not hold up the other streams' launches
+            def drive(lane: int):
+                with torch.cuda.stream(lanes[lane]):
+                    for vi in mine[lane::n_lanes]:
+                        one_view(vi, lane)
+
+            with ThreadPoolExecutor(max_workers=n_lanes) as pool:
+                for f in [pool.submit(drive, lane) for lane in range(n_lanes)]:
+                    f.result()
+        else:
+            for j, vi in enumerate(mine):
+                with torch.cuda.stream(lanes[j % n_lanes]):
+                    one_view(vi, j % n_lanes)
         for st in lanes:
             cur.wait_stream(st)
     loss_sum = losses[0]
@@ -182,15 +195,3 @@ def download_grads(params: GaussianParams, host_grads: torch.Tensor, rank: int =
     host_grads[lo:hi].copy_(params.grad_bucket[lo:hi], non_blocking=True)
     return (hi - lo) * 4
 
-
-_LANE_STREAMS: Dict[object, list] = {}
-
-
-def _lane_streams(dev: torch.device, n: int):
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
-    pool = _LANE_STREAMS.setdefault(key, [])
-    while len(pool) < n:
-        # high priority: the library then moves its blend kernels to a lowest-priority companion stream,
-        # so the small kernels of one view are dispatched underneath another view's blend grid
-        pool.append(torch.cuda.Stream(device=dev, priority=-1))
-    return pool[:n]

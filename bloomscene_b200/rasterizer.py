@@ -9,6 +9,7 @@ exercise identical Python on both sides.
 """
 from __future__ import annotations
 
+from concurrent.futures import ThreadPoolExecutor
 from types import SimpleNamespace
 from typing import NamedTuple
 
@@ -56,6 +57,21 @@ def _guarded(native_fn, args, debug: bool, dump_file: str, message: str):
         torch.save(snapshot, dump_file)
         print(message)
         raise
+
+
+_LANE_STREAMS = {}
+
+
+def lane_streams(dev: torch.device, n: int):
+    """`n` long-lived high-priority CUDA streams of `dev` that a batch of views is dealt onto.  High
+    priority makes the library move its blend kernels to a lowest-priority companion stream
+    (brs_blend_companion_stream), so the small kernels of one view are dispatched underneath another
+    view's blend grid."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    pool = _LANE_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev, priority=-1))
+    return pool[:n]
 
 
 def bind(_C) -> SimpleNamespace:
@@ -168,8 +184,76 @@ def bind(_C) -> SimpleNamespace:
                                                     opt(cov3D_precomp), rs.viewmatrix, rs.projmatrix, rs.tanfovx,
                                                     rs.tanfovy, rs.image_height, rs.image_width, rs.prefiltered, rs.debug)
 
+    def render_views(raster_settings_list, means3D, opacities, shs=None, colors_precomp=None, scales=None,
+                     rotations=None, cov3D_precomp=None, streams=4, keep_radii=False, host_threads=True):
+        """Forward-only render of one Gaussian set from a list of cameras (BloomScene's render_video loop,
+        reference bloomscene.py:191-204, one `GaussianRasterizer` call per frame there).  Extension: no
+        autograd graph, no saved state, and on a GPU the views are dealt onto `streams` CUDA streams so that
+        one view's preprocess / sort / binning kernels and its host wait for the instance count run under
+        another view's blend; with `host_threads` every stream is driven by its own host thread (the native
+        forward releases the GIL).  Returns (color [B,3,H,W], depth [B,1,H,W], radii list or None); every view's
+        result is bit-identical to a single `GaussianRasterizer` call with the same settings."""
+        views = list(raster_settings_list)
+        if (shs is None) == (colors_precomp is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        has_any_sr, has_both_sr = (scales is not None or rotations is not None), (scales is not None and rotations is not None)
+        if (not has_both_sr and cov3D_precomp is None) or (has_any_sr and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        opt = lambda t: _absent() if t is None else t.detach()
+        dev = means3D.device
+        B = len(views)
+        H, W = (views[0].image_height, views[0].image_width) if B else (0, 0)
+        color = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        radii = [None] * B if keep_radii else None
+        m3, op = means3D.detach(), opacities.detach()
+        sh_, cp_, sc_, ro_, cv_ = opt(shs), opt(colors_precomp), opt(scales), opt(rotations), opt(cov3D_precomp)
+
+        def one(j, rs):
+            if (rs.image_height, rs.image_width) != (H, W):
+                raise Exception('render_views: all views of a batch must share one resolution')
+            out = _C.rasterize_gaussians(rs.bg, m3, cp_, op, sc_, ro_, rs.scale_modifier, cv_, rs.viewmatrix,
+                                         rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh_,
+                                         rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+            color[j].copy_(out[1])
+            depth[j].copy_(out[2])
+            if keep_radii:
+                radii[j] = out[3]
+
+        with torch.no_grad():
+            n_lanes = max(1, min(int(streams), B)) if dev.type == "cuda" else 1
+            if n_lanes == 1:
+                for j, rs in enumerate(views):
+                    one(j, rs)
+            else:
+                cur = torch.cuda.current_stream(dev)
+                lanes = lane_streams(dev, n_lanes)
+                for st in lanes:
+                    st.wait_stream(cur)  # inputs and the output stacks were produced on the caller's stream
+
+                def drive(lane):  # one host thread per stream: the native forward releases the GIL while it
+                    with torch.no_grad(), torch.cuda.stream(lanes[lane]):  # waits and launches
+                        for j in range(lane, B, n_lanes):
+                            one(j, views[j])
+
+                if host_threads:
+                    with ThreadPoolExecutor(max_workers=n_lanes) as pool:
+                        for f in [pool.submit(drive, lane) for lane in range(n_lanes)]:
+                            f.result()
+                else:
+                    for j, rs in enumerate(views):
+                        with torch.cuda.stream(lanes[j % n_lanes]):
+                            one(j, rs)
+                for st in lanes:
+                    cur.wait_stream(st)
+                if keep_radii:
+                    for r in radii:
+                        r.record_stream(cur)  # allocated on a lane stream, consumed on the caller's
+        return color, depth, radii
+
     return SimpleNamespace(
         _C=_C,
+        render_views=render_views,
         _RasterizeGaussians=_RasterizeGaussians,
         rasterize_gaussians=rasterize_gaussians,
         GaussianRasterizer=GaussianRasterizer,

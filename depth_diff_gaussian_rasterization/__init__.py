@@ -9,4 +9,5 @@ from bloomscene_b200 import (  # noqa: F401
     _RasterizeGaussians,
     cpu_deep_copy_tuple,
     rasterize_gaussians,
+    render_views,
 )

@@ -7,4 +7,5 @@ from depth_diff_gaussian_rasterization import (  # noqa: F401
     _C,
     _RasterizeGaussians,
     rasterize_gaussians,
+    render_views,
 )

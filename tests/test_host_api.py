@@ -157,3 +157,30 @@ def test_autograd_plumbing_with_oracle_backend():
     (color * Wc).sum().backward()
     fd = (pert - base) / 1e-2
     assert abs(fd - op.grad[i].item()) <= 0.1 * abs(fd) + 1e-2
+
+
+def test_render_views_equals_single_view_calls_with_oracle_backend():
+    """render_views (forward-only batch entry point) returns exactly what one GaussianRasterizer call per view returns."""
+    from bloomscene_b200 import synthetic
+    from bloomscene_b200.rasterizer import GaussianRasterizationSettings, bind
+    from oracle_backend import OracleBackend
+
+    api = bind(OracleBackend())
+    scene = synthetic.make_scene(300, "object", "precomp", -3.0, seed=4)
+    bg = torch.tensor([0.2, 0.1, 0.0])
+    settings = [synthetic.raster_settings(synthetic.orbit_camera(40, 24, 0.7 * k), 0, bg, GaussianRasterizationSettings)
+                for k in range(3)]
+    color, depth, radii = api.render_views(settings, scene.means3D, scene.opacities, colors_precomp=scene.colors_precomp,
+                                           scales=scene.scales, rotations=scene.rotations, keep_radii=True)
+    assert color.shape == (3, 3, 24, 40) and depth.shape == (3, 1, 24, 40) and len(radii) == 3
+    for k, rs in enumerate(settings):
+        c, r, d = api.GaussianRasterizer(rs)(scene.means3D, torch.zeros_like(scene.means3D), scene.opacities,
+                                             colors_precomp=scene.colors_precomp, scales=scene.scales,
+                                             rotations=scene.rotations)
+        assert torch.equal(c, color[k]) and torch.equal(d, depth[k]) and torch.equal(r, radii[k])
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        api.render_views(settings, scene.means3D, scene.opacities, scales=scene.scales, rotations=scene.rotations)
+    with pytest.raises(Exception, match="share one resolution"):
+        other = synthetic.raster_settings(synthetic.orbit_camera(32, 24, 0.1), 0, bg, GaussianRasterizationSettings)
+        api.render_views(settings + [other], scene.means3D, scene.opacities, colors_precomp=scene.colors_precomp,
+                         scales=scene.scales, rotations=scene.rotations)

@@ -47,6 +47,20 @@ def render_loop(api, scene, cams, bg, reps=1):
     return dt / (reps * len(cams)) * 1e3, out
 
 
+def render_batched(api, scene, cams, bg, streams=4, reps=3, host_threads=True):
+    """The same frames through the forward-only batch entry point (render_views: views dealt onto CUDA streams)."""
+    settings = [synthetic.raster_settings(cam, scene.sh_degree, bg, api.GaussianRasterizationSettings) for cam in cams]
+    kw = dict(shs=scene.shs, colors_precomp=scene.colors_precomp, scales=scene.scales, rotations=scene.rotations, streams=streams,
+              host_threads=host_threads)
+    api.render_views(settings[:streams], scene.means3D, scene.opacities, **kw)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = api.render_views(settings, scene.means3D, scene.opacities, **kw)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / (reps * len(cams)) * 1e3, out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="A,B,C,D")
@@ -77,11 +91,17 @@ def main():
             ms, out = render_loop(mine, scene, cams, bg)
             rec["ours"] = {"fwd_ms_per_view": round(ms, 4), "views_per_s": round(1e3 / ms, 1), "views_timed": len(cams),
                            "visible_last_view": int((out[1] > 0).sum())}
+            ms_b, outb = render_batched(mine, scene, cams, bg)
+            rec["ours_render_views_4_streams"] = {"fwd_ms_per_view": round(ms_b, 4), "views_per_s": round(1e3 / ms_b, 1),
+                                                  "last_frame_equal_to_loop": bool(torch.equal(outb[0][-1], out[0]))}
+            ms_b1, _ = render_batched(mine, scene, cams, bg, host_threads=False)
+            rec["ours_render_views_4_streams"]["fwd_ms_per_view_one_host_thread"] = round(ms_b1, 4)
             if ref is not None:
                 render_loop(ref, scene, cams[:3], bg)
                 ms_r, _ = render_loop(ref, scene, cams, bg)
                 rec["reference_cuda"] = {"fwd_ms_per_view": round(ms_r, 4), "views_per_s": round(1e3 / ms_r, 1)}
                 rec["speedup_fwd"] = round(ms_r / ms, 2)
+                rec["speedup_fwd_render_views"] = round(ms_r / ms_b, 2)
                 worst = {"radii_mismatch": 0, "color_maxabs": 0.0, "depth_maxabs": 0.0, "R_equal": True}
                 for cam in cams[:4]:
                     o = mine._C.rasterize_gaussians(*pl.forward_args(scene, cam, bg))

@@ -617,7 +617,8 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
                  const float* dL_dout_color, const float* dL_dout_depth, const brs_grads* grads, brs_alloc_fn alloc,
                  void* alloc_ctx, brs_stream stream)
 {
-	(void)dL_dout_depth; // reference: plumbed, never used (backward.cu:443-554)
+	// reference: dL_dout_depth is plumbed and never used (backward.cu:443-554); it is read only when
+	// the caller opts in with brs_grads.depth_gradient
 	int st = validate_view(view, true);
 	if (st != BRS_OK)
 		return st;
@@ -647,6 +648,9 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 		return BRS_ERR_STATE;
 	if ((size_t)W * H > 0 && dL_dout_color == nullptr)
 		return BRS_ERR_INVALID_ARG;
+	const bool depth_grad = grads->depth_gradient != 0;
+	if (depth_grad && (size_t)W * H > 0 && (dL_dout_depth == nullptr || grads->out_depth == nullptr))
+		return BRS_ERR_INVALID_ARG;
 	const bool debug = view->debug != 0;
 	const uint32_t grid_x = (W + TILE_X - 1) / TILE_X, grid_y = (H + TILE_Y - 1) / TILE_Y;
 
@@ -671,6 +675,8 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 		bb.final_T = reinterpret_cast<const float*>(image + il.final_T);
 		bb.n_contrib = reinterpret_cast<const uint32_t*>(image + il.n_contrib);
 		bb.dL_dpixels = dL_dout_color;
+		bb.dL_ddepth = depth_grad ? dL_dout_depth : nullptr;
+		bb.out_depth = depth_grad ? grads->out_depth : nullptr;
 		bb.accum = accum;
 		if (Companion* c = debug ? nullptr : companion_for(stream)) {
 			BRS_CUDA(cudaEventRecord(c->before, stream));
@@ -705,6 +711,7 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 	pb.focal_x = W / (2.0f * view->tanfovx);
 	pb.accum = accum;
 	pb.accumulate = acc ? 1 : 0;
+	pb.depth_gradient = depth_grad ? 1 : 0;
 	pb.dL_dmeans2D = grads->dL_dmeans2D;
 	pb.dL_dcolors = grads->dL_dcolors;
 	pb.dL_dopacity = grads->dL_dopacity;

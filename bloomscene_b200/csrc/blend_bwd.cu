@@ -50,6 +50,7 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 
 // Flush `cnt` (<= GROUP) staged records of this warp.  Lane (r = lane >> 2, q = lane & 3) owns
 // record r and the q-th row (8 pixels) of the warp's pixel block.
+template <bool DEPTH>
 __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int cnt,
                                             const StagedRecord* __restrict__ rec, const uint32_t* __restrict__ s_id,
                                             const float* __restrict__ s_dpx, float bxf, float byf, uint32_t lane,
@@ -58,9 +59,9 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int
 	__syncwarp();
 	const uint32_t r = lane >> 2, q = lane & 3;
 	const bool live = (int)r < cnt;
-	float v[9];
+	float v[10]; // v[9]: dL_dz, only with DEPTH
 #pragma unroll
-	for (int i = 0; i < 9; i++)
+	for (int i = 0; i < 10; i++)
 		v[i] = 0.f;
 	uint32_t id = 0;
 	if (live) {
@@ -84,9 +85,10 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int
 			Sxx = fmaf(t, dx, Sxx);
 		}
 		const float4* dp = reinterpret_cast<const float4*>(s_dpx + q * 8);
-		float c[3];
+		constexpr int NCH = DEPTH ? 4 : 3; // with DEPTH the 4th row of s_dpx holds gD = dL_dD
+		float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-		for (int ch = 0; ch < 3; ch++) {
+		for (int ch = 0; ch < NCH; ch++) {
 			const float4 da = dp[ch * 8], db = dp[ch * 8 + 1];
 			float s = u[0] * da.x;
 			s = fmaf(u[1], da.y, s);
@@ -110,6 +112,7 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int
 		v[6] = c[0];
 		v[7] = c[1];
 		v[8] = c[2];
+		v[9] = c[3];
 	}
 	// combine the 4 rows (lanes q = 0..3 of a record): 9 -> 5 -> 3 values per lane, 8 shuffles.
 	// Afterwards lane q holds slots 2q, 2q + 1 in (a, b) and every lane holds slot 8 in c8.
@@ -134,21 +137,38 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int
 		b = keep + __shfl_xor_sync(0xffffffffu, send, 1);
 	}
 	c8 += __shfl_xor_sync(0xffffffffu, c8, 1);
+	float c9 = 0.f;
+	if (DEPTH) {
+		c9 = v[9] + __shfl_xor_sync(0xffffffffu, v[9], 2);
+		c9 += __shfl_xor_sync(0xffffffffu, c9, 1);
+	}
 	if (live) {
 		float* dst = accum + (size_t)id * ACCUM_STRIDE;
 		red_add_v2(dst + 2 * q, a, b);
-		if (q == 0)
-			atomicAdd(dst + 8, c8);
+		if (q == 0) {
+			if (DEPTH)
+				red_add_v2(dst + 8, c8, c9);
+			else
+				atomicAdd(dst + 8, c8);
+		}
 	}
 	__syncwarp();
 }
 
+// DEPTH (extension, off by default = the reference): the depth image carries gradient too.  The forward's
+// depth is D / acc (D = sum T alpha z, acc = 1e-6 + sum T alpha, gate acc > 0.5: forward.cu:464-468), so
+// D and acc join the recurrence as two more blended channels with per-Gaussian values z and 1, pixel
+// gradients gD = g / acc and gA = -g depth / acc and no background term — the shape of the reference's
+// commented-out depth lines (backward.cu:539-542) plus the normalisation they lack.  In the scalar
+// recurrence this only extends cd = colour . dL_dpixel by z gD + gA; z collects dL_dz = S(u gD) in
+// accumulator slot 9.  acc is recovered as 1e-6 + (1 - T_final) (sum T alpha telescopes to 1 - T_final).
+template <bool DEPTH>
 __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdArgs a)
 {
 	__shared__ StagedRecord s_rec[2][BATCH];
 	__shared__ uint32_t s_ids[2][BATCH];
 	__shared__ __align__(16) float s_stage[BLEND_WARPS][GROUP * STAGE_STRIDE];
-	__shared__ __align__(16) float s_dpx[BLEND_WARPS][3 * 32];
+	__shared__ __align__(16) float s_dpx[BLEND_WARPS][(DEPTH ? 4 : 3) * 32];
 	__shared__ uint32_t s_max[BLEND_WARPS];
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -178,6 +198,19 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	s_dpx[warp][lane] = dpx0;
 	s_dpx[warp][32 + lane] = dpx1;
 	s_dpx[warp][64 + lane] = dpx2;
+	float gD = 0.f, gA = 0.f;
+	if (DEPTH) {
+		if (inside) {
+			const float depth = __ldg(a.out_depth + pix_id);
+			if (depth > 0.f) { // the forward's acc > 0.5 gate (view-space z > 0.2, so D / acc > 0 exactly when it passed)
+				const float acc = 0.000001f + (1.0f - T_final);
+				const float g_over_acc = __fdividef(__ldg(a.dL_ddepth + pix_id), acc);
+				gD = g_over_acc;
+				gA = -g_over_acc * depth;
+			}
+		}
+		s_dpx[warp][96 + lane] = gD;
+	}
 
 	// records at list positions >= max(n_contrib) are skipped by every pixel of the warp / tile
 	int warp_max = last_contributor;
@@ -272,7 +305,9 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 					// needed, so the recurrence runs on its projection: beta = accum_rec . dL_dpixel and
 					// cd = colour . dL_dpixel are scalars.
 					beta = fmaf(last_alpha, last_cd - beta, beta);
-					const float cd = fmaf(col.z, dpx2, fmaf(col.y, dpx1, col.x * dpx0));
+					float cd = fmaf(col.z, dpx2, fmaf(col.y, dpx1, col.x * dpx0));
+					if (DEPTH)
+						cd = fmaf(col.w, gD, cd) + gA;
 					float dL_dalpha = (cd - beta) * T;
 					last_cd = cd;
 					last_alpha = alpha;
@@ -285,7 +320,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 					st[64] = __int_as_float(idx); // the record's batch slot rides in the row's padding
 				st += STAGE_STRIDE;
 				if (++staged == GROUP) {
-					flush_group(stage, GROUP, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
+					flush_group<DEPTH>(stage, GROUP, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 					staged = 0;
 					st = stage + lane;
 				}
@@ -293,7 +328,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 		}
 		// staged slots refer to this batch's shared records: flush before they are overwritten
 		if (staged) {
-			flush_group(stage, staged, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
+			flush_group<DEPTH>(stage, staged, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 			staged = 0;
 			st = stage + lane;
 		}
@@ -311,7 +346,10 @@ cudaError_t launch_blend_backward(const BlendBwdArgs& args, cudaStream_t stream)
 	if (a.W <= 0 || a.H <= 0)
 		return cudaSuccess;
 	dim3 grid(a.grid_x, a.grid_y, 1);
-	blend_backward_kernel<<<grid, BLEND_THREADS, 0, stream>>>(a);
+	if (a.dL_ddepth != nullptr && a.out_depth != nullptr)
+		blend_backward_kernel<true><<<grid, BLEND_THREADS, 0, stream>>>(a);
+	else
+		blend_backward_kernel<false><<<grid, BLEND_THREADS, 0, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
 }

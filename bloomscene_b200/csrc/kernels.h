@@ -118,7 +118,9 @@ struct BlendBwdArgs {
 	const float* final_T;
 	const uint32_t* n_contrib;
 	const float* dL_dpixels; // [3,H,W]
-	float* accum;            // [P][12] fp32, pre-zeroed: {dmean2D.x, .y, dconic.x, .y, .w, dopacity, dcol r,g,b, pad x3}
+	const float* dL_ddepth;  // [H,W]; with out_depth: opt-in depth gradient (brs_grads.depth_gradient), else nullptr
+	const float* out_depth;  // [H,W] the forward's depth output
+	float* accum;            // [P][12] fp32, pre-zeroed: {dmean2D.x, .y, dconic.x, .y, .w, dopacity, dcol r,g,b, dz, pad x2}
 };
 cudaError_t launch_blend_backward(const BlendBwdArgs& a, cudaStream_t stream);
 
@@ -139,6 +141,7 @@ struct PreprocessBwdArgs {
 	float tan_fovx, tan_fovy, focal_x, focal_y;
 	const float* accum; // [P][12] from the blend backward
 	int accumulate;     // 0: every output element is written; 1: see brs_grads.accumulate
+	int depth_gradient; // 1: accum slot 9 holds dL_dz (view-space depth) and feeds dL_dmeans3D
 	int fact_offset;    // (set by the launcher) float offset of the basis-factor rows in dynamic shared memory
 	// outputs
 	float* dL_dmeans2D;   // [P,3]

@@ -370,6 +370,13 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 		o_mean3D.x += dm.x;
 		o_mean3D.y += dm.y;
 		o_mean3D.z += dm.z;
+		if (a.depth_gradient) {
+			// opt-in depth gradient: z = p_view.z = view[2] x + view[6] y + view[10] z + view[14] (forward.cu:186)
+			const float dz = a2.y;
+			o_mean3D.x += view[2] * dz;
+			o_mean3D.y += view[6] * dz;
+			o_mean3D.z += view[10] * dz;
+		}
 
 		if (a.shs != nullptr) {
 			const v3 pos = make_v3(mean.x, mean.y, mean.z);

@@ -155,8 +155,20 @@ void run_backward(const torch::Tensor& background, const torch::Tensor& means3D,
                   const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth, const torch::Tensor& sh,
                   const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
                   const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug, const int M,
-                  const brs_grads& grads, const char* what)
+                  const brs_grads& grads_in, const char* what,
+                  const c10::optional<torch::Tensor>& out_depth = c10::nullopt)
 {
+	brs_grads grads = grads_in;
+	torch::Tensor out_depth_c;
+	if (out_depth.has_value() && out_depth->defined() && out_depth->numel() != 0) {
+		// opt-in depth gradient (brs_grads.depth_gradient): needs the forward's depth image and dL_dout_depth
+		TORCH_CHECK(out_depth->is_cuda() && out_depth->scalar_type() == torch::kFloat32, "out_depth must be CUDA float32");
+		TORCH_CHECK(dL_dout_depth.defined() && dL_dout_depth.numel() == out_depth->numel(),
+		            "depth gradient: dL_dout_depth must have the shape of out_depth");
+		out_depth_c = out_depth->contiguous();
+		grads.out_depth = out_depth_c.data_ptr<float>();
+		grads.depth_gradient = 1;
+	}
 	const int P = means3D.size(0);
 	const int H = dL_dout_color.size(1);
 	const int W = dL_dout_color.size(2);
@@ -230,7 +242,8 @@ float* sink_ptr(const c10::optional<torch::Tensor>& t, int64_t numel, const char
 
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
            torch::Tensor>
-RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D,
+RasterizeGaussiansBackwardImpl(const c10::optional<torch::Tensor>& out_depth, const torch::Tensor& background,
+                               const torch::Tensor& means3D,
                                const torch::Tensor& radii, const torch::Tensor& colors, const torch::Tensor& scales,
                                const torch::Tensor& rotations, const float scale_modifier,
                                const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
@@ -268,11 +281,45 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
 		grads.accumulate = 0;
 		run_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
 		             projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth, sh, degree, campos, geomBuffer, R,
-		             binningBuffer, imageBuffer, debug, M, grads, "rasterize_gaussians_backward");
+		             binningBuffer, imageBuffer, debug, M, grads, "rasterize_gaussians_backward", out_depth);
 	}
 
 	return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
 	                       dL_drotations);
+}
+
+using GradTuple = std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+                             torch::Tensor, torch::Tensor>;
+
+// reference binding (rasterize_points.h:42-66): 22 arguments, depth carries no gradient
+GradTuple RasterizeGaussiansBackwardCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
+    const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+    const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+    const float tan_fovx, const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& sh, const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug)
+{
+	return RasterizeGaussiansBackwardImpl(c10::nullopt, background, means3D, radii, colors, scales, rotations,
+	                                      scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+	                                      dL_dout_color, dL_dout_depth, sh, degree, campos, geomBuffer, R, binningBuffer,
+	                                      imageBuffer, debug);
+}
+
+// Extension (opt-in): the same 22 arguments plus the forward's depth image; dL_dout_depth
+// is then back-propagated (brs_grads.depth_gradient).
+GradTuple RasterizeGaussiansBackwardDepthCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
+    const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+    const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+    const float tan_fovx, const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& sh, const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug, const torch::Tensor& out_depth)
+{
+	return RasterizeGaussiansBackwardImpl(out_depth, background, means3D, radii, colors, scales, rotations, scale_modifier,
+	                                      cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+	                                      dL_dout_depth, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer,
+	                                      debug);
 }
 
 // Extension (no reference counterpart): the same backward, but the parameter gradients are ADDED in
@@ -289,7 +336,7 @@ torch::Tensor RasterizeGaussiansBackwardAccumulateCUDA(
     const c10::optional<torch::Tensor>& sink_means3D, const c10::optional<torch::Tensor>& sink_colors,
     const c10::optional<torch::Tensor>& sink_opacity, const c10::optional<torch::Tensor>& sink_cov3D,
     const c10::optional<torch::Tensor>& sink_sh, const c10::optional<torch::Tensor>& sink_scales,
-    const c10::optional<torch::Tensor>& sink_rotations)
+    const c10::optional<torch::Tensor>& sink_rotations, const c10::optional<torch::Tensor>& out_depth)
 {
 	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
 	c10::cuda::CUDAGuard guard(means3D.device());
@@ -309,7 +356,7 @@ torch::Tensor RasterizeGaussiansBackwardAccumulateCUDA(
 		grads.accumulate = 1;
 		run_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
 		             projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth, sh, degree, campos, geomBuffer, R,
-		             binningBuffer, imageBuffer, debug, M, grads, "rasterize_gaussians_backward_accumulate");
+		             binningBuffer, imageBuffer, debug, M, grads, "rasterize_gaussians_backward_accumulate", out_depth);
 	}
 	return dL_dmeans2D;
 }
@@ -470,6 +517,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
 	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
 	m.def("rasterize_gaussians_backward_accumulate", &RasterizeGaussiansBackwardAccumulateCUDA,
+	      pybind11::call_guard<pybind11::gil_scoped_release>());
+	m.def("rasterize_gaussians_backward_depth", &RasterizeGaussiansBackwardDepthCUDA,
 	      pybind11::call_guard<pybind11::gil_scoped_release>());
 	m.def("rasterize_aussians_filter", &RasterizeGaussiansfilterCUDA);
 	m.def("mark_visible", &markVisible);

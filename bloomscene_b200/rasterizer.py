@@ -83,7 +83,7 @@ def bind(_C) -> SimpleNamespace:
 
         @staticmethod
         def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                    raster_settings, grad_sink=None):
+                    raster_settings, grad_sink=None, depth_gradient=False):
             rs = raster_settings
             out = _guarded(
                 _C.rasterize_gaussians,
@@ -96,14 +96,18 @@ def bind(_C) -> SimpleNamespace:
             ctx.raster_settings = rs
             ctx.grad_sink = grad_sink
             ctx.num_rendered = num_rendered
+            ctx.depth_gradient = bool(depth_gradient)
+            # extension: with depth_gradient the backward also needs the depth image the forward produced
+            extra = (depth,) if depth_gradient else ()
             ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom,
-                                  binning, image)
+                                  binning, image, *extra)
             return color, radii, depth
 
         @staticmethod
         def backward(ctx, grad_out_color, grad_radii, grad_depth):
             rs = ctx.raster_settings
-            colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, image = ctx.saved_tensors
+            colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, image = ctx.saved_tensors[:10]
+            out_depth = ctx.saved_tensors[10] if ctx.depth_gradient else None
             if ctx.grad_sink is not None:
                 # extension: parameter gradients are added in place to the caller's sinks by the kernel
                 # (brs_grads.accumulate); autograd only carries the per-view means2D gradient
@@ -113,8 +117,16 @@ def bind(_C) -> SimpleNamespace:
                     rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, sh, rs.sh_degree,
                     rs.campos, geom, ctx.num_rendered, binning, image, rs.debug,
                     k.get("means3D"), k.get("colors_precomp"), k.get("opacities"), k.get("cov3D_precomp"), k.get("shs"),
-                    k.get("scales"), k.get("rotations"))
-                return None, d_means2D, None, None, None, None, None, None, None, None
+                    k.get("scales"), k.get("rotations"), out_depth)
+                return None, d_means2D, None, None, None, None, None, None, None, None, None
+            if ctx.depth_gradient:
+                # extension: grad_depth is back-propagated through the depth image (default off = reference)
+                g = _C.rasterize_gaussians_backward_depth(
+                    rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                    rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, sh, rs.sh_degree,
+                    rs.campos, geom, ctx.num_rendered, binning, image, rs.debug, out_depth)
+                d_means2D, d_colors, d_opacities, d_means3D, d_cov3D, d_sh, d_scales, d_rotations = g
+                return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None, None
             g = _guarded(
                 _C.rasterize_gaussians_backward,
                 (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
@@ -125,13 +137,16 @@ def bind(_C) -> SimpleNamespace:
             d_means2D, d_colors, d_opacities, d_means3D, d_cov3D, d_sh, d_scales, d_rotations = g
             # one gradient per autograd input, in input order (reference __init__.py:144-154);
             # grad_radii carries nothing and grad_depth is plumbed down but unused by the kernels
-            return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None
+            return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None, None
 
     has_sink = hasattr(_C, "rasterize_gaussians_backward_accumulate")
+    has_depth_grad = hasattr(_C, "rasterize_gaussians_backward_depth")
 
     def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                            raster_settings, grad_sink=None):
-        # reference __init__.py:21-42; `grad_sink` is an extension (see GaussianRasterizer)
+                            raster_settings, grad_sink=None, depth_gradient=False):
+        # reference __init__.py:21-42; `grad_sink` and `depth_gradient` are extensions (see GaussianRasterizer)
+        if depth_gradient and not has_depth_grad:
+            raise Exception('this native module has no depth gradient (the reference comments it out)')
         if grad_sink is not None:
             if not has_sink:
                 raise Exception('this native module has no in-place gradient accumulation (grad_sink)')
@@ -141,7 +156,7 @@ def bind(_C) -> SimpleNamespace:
                 if t.numel() != 0 and t.requires_grad and name not in grad_sink:
                     raise Exception(f'grad_sink has no entry for {name}, whose gradient would be dropped')
         return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                         cov3Ds_precomp, raster_settings, grad_sink)
+                                         cov3Ds_precomp, raster_settings, grad_sink, depth_gradient)
 
     class GaussianRasterizer(nn.Module):
         """reference __init__.py:172-249: forward / visible_filter / markVisible with the same signatures.
@@ -150,14 +165,22 @@ def bind(_C) -> SimpleNamespace:
         "shs" | "colors_precomp", "scales", "rotations" | "cov3D_precomp") to contiguous fp32 tensors of the
         inputs' shapes.  With it, backward ADDS those inputs' gradients to the sinks inside the kernel and
         autograd receives None for them — a multi-view step accumulates straight into its allreduce bucket
-        instead of materialising (44 + 12 M) bytes per Gaussian per view and adding them afterwards."""
+        instead of materialising (44 + 12 M) bytes per Gaussian per view and adding them afterwards.
+
+        Extension: `depth_gradient` (default False = reference behaviour, where the depth output carries no
+        gradient because every depth line of the reference's backward is commented out, backward.cu:443-554).
+        With it, the gradient of the returned depth image flows back through D / acc (and its acc > 0.5
+        gate, forward.cu:464-468) into opacities, means3D and scales / rotations | cov3D_precomp, so
+        BloomScene's depth losses (bloomscene.py:298-325) can act on the geometry."""
 
         supports_grad_sink = has_sink
+        supports_depth_gradient = has_depth_grad
 
-        def __init__(self, raster_settings, grad_sink=None):
+        def __init__(self, raster_settings, grad_sink=None, depth_gradient=False):
             super().__init__()
             self.raster_settings = raster_settings
             self.grad_sink = grad_sink
+            self.depth_gradient = depth_gradient
 
         def markVisible(self, positions):
             rs = self.raster_settings
@@ -174,7 +197,8 @@ def bind(_C) -> SimpleNamespace:
                 raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
             opt = lambda t: _absent() if t is None else t
             return rasterize_gaussians(means3D, means2D, opt(shs), opt(colors_precomp), opacities, opt(scales),
-                                       opt(rotations), opt(cov3D_precomp), self.raster_settings, self.grad_sink)
+                                       opt(rotations), opt(cov3D_precomp), self.raster_settings, self.grad_sink,
+                                       self.depth_gradient)
 
         def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
             rs = self.raster_settings

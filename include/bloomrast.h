@@ -117,6 +117,15 @@ typedef struct brs_grads {
 	 * buffers hold, for visible Gaussians only; tensors of absent inputs may be NULL and are not
 	 * touched; dL_dmeans2D (a per-view statistic) is still overwritten. */
 	int accumulate;
+	/* 0 (reference behaviour): the depth image carries no gradient, dL_dout_depth is ignored — the
+	 * reference has every depth line of its backward commented out (backward.cu:443-554).
+	 * 1 (extension): dL_dout_depth [1,H,W] is back-propagated through the depth the
+	 * forward actually outputs — D / acc with D = sum T alpha z, acc = 1e-6 + sum T alpha, zero where
+	 * acc <= 0.5 (forward.cu:464-468) — into opacity, means2D, conic and the view-space depth z of every
+	 * Gaussian, i.e. into means3D, scales / rotations | cov3D_precomp and opacities.  `out_depth` must
+	 * then be the [1,H,W] depth image brs_forward wrote for this state. */
+	int depth_gradient;
+	const float* out_depth;
 } brs_grads;
 
 /* --- entry points ------------------------------------------------------------------------- */
@@ -132,8 +141,9 @@ int brs_forward(const brs_view* view, const brs_gaussians* g,
                 brs_fwd_state* state, brs_stream stream);
 
 /* Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:78-105, rasterizer_impl.cu:403-504).
- * dL_dout_depth is accepted and ignored: the reference plumbs it but every use is commented out
- * (backward.cu:443-554), so depth carries no gradient.  No host synchronisation. */
+ * dL_dout_depth is accepted and, unless grads->depth_gradient is set, ignored: the reference plumbs it
+ * but every use is commented out (backward.cu:443-554), so depth carries no gradient by default.
+ * No host synchronisation. */
 int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
                  const brs_fwd_state* state,
                  const float* dL_dout_color, const float* dL_dout_depth,

@@ -72,6 +72,8 @@ def lib():
         L.orc_forward.restype = C.c_int
         L.orc_backward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Grads)]
         L.orc_backward.restype = C.c_int
+        L.orc_backward_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Grads)]
+        L.orc_backward_ex.restype = C.c_int
         L.orc_visible_filter.argtypes = [C.POINTER(_Inputs), C.c_int, C.c_void_p]
         L.orc_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
@@ -148,17 +150,20 @@ class Oracle:
         R = self.L.orc_forward(self.ctx, C.byref(inp), _ptr(color), _ptr(depth), _ptr(radii))
         return R, color, depth, radii
 
-    def backward(self, dL_dcolor) -> Dict[str, np.ndarray]:
-        """Gradients in the reference's shapes (rasterize_points.cu:154-162). Call after forward()."""
+    def backward(self, dL_dcolor, dL_ddepth=None) -> Dict[str, np.ndarray]:
+        """Gradients in the reference's shapes (rasterize_points.cu:154-162). Call after forward().
+        `dL_ddepth` (default None = the reference: depth carries no gradient) switches on the opt-in
+        depth-gradient extension."""
         P, M = self.P, self.M
         d = _f32(dL_dcolor)
+        dd = _f32(dL_ddepth) if dL_ddepth is not None else None
         g = {"dL_dmeans2D": np.zeros((P, 3), np.float32), "dL_dcolors": np.zeros((P, 3), np.float32),
              "dL_dopacity": np.zeros((P, 1), np.float32), "dL_dmeans3D": np.zeros((P, 3), np.float32),
              "dL_dcov3D": np.zeros((P, 6), np.float32), "dL_dsh": np.zeros((P, M, 3), np.float32),
              "dL_dscales": np.zeros((P, 3), np.float32), "dL_drotations": np.zeros((P, 4), np.float32)}
         gs = _Grads(*[_ptr(g[n]) if g[n].size else None for n, _ in _Grads._fields_])
         if P:
-            self.L.orc_backward(self.ctx, _ptr(d), C.byref(gs))
+            self.L.orc_backward_ex(self.ctx, _ptr(d), _ptr(dd), C.byref(gs))
         return g
 
     def visible_filter(self, scales_stride: int = 3, **kw) -> np.ndarray:

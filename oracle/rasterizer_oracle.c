@@ -140,6 +140,7 @@ typedef struct orc_ctx {
 	uint32_t* ranges; /* [tiles][2] */
 	float* final_T;
 	uint32_t* n_contrib;
+	float *acc_final, *D_final; /* per pixel: the forward's accumulated weight and un-normalised depth (opt-in depth gradient) */
 	long long pairs_evaluated, pairs_contributing; /* E and C of SURVEY.md §8(d) */
 } orc_ctx;
 
@@ -149,10 +150,10 @@ static void free_state(orc_ctx* c)
 {
 	free(c->depths); free(c->clamped); free(c->radii); free(c->means2D); free(c->cov3D); free(c->conic_opacity);
 	free(c->rgb); free(c->tiles_touched); free(c->point_offsets); free(c->keys_unsorted); free(c->keys);
-	free(c->values_unsorted); free(c->values); free(c->ranges); free(c->final_T); free(c->n_contrib);
+	free(c->values_unsorted); free(c->values); free(c->ranges); free(c->final_T); free(c->n_contrib); free(c->acc_final); free(c->D_final);
 	c->depths = NULL; c->clamped = NULL; c->radii = NULL; c->means2D = NULL; c->cov3D = NULL; c->conic_opacity = NULL;
 	c->rgb = NULL; c->tiles_touched = NULL; c->point_offsets = NULL; c->keys_unsorted = NULL; c->keys = NULL;
-	c->values_unsorted = NULL; c->values = NULL; c->ranges = NULL; c->final_T = NULL; c->n_contrib = NULL;
+	c->values_unsorted = NULL; c->values = NULL; c->ranges = NULL; c->final_T = NULL; c->n_contrib = NULL; c->acc_final = NULL; c->D_final = NULL;
 }
 
 void orc_destroy(orc_ctx* c)
@@ -406,6 +407,8 @@ static void render_pixel(const orc_ctx* c, int px, int py, uint32_t start, uint3
 	}
 	c->final_T[pix_id] = T;
 	c->n_contrib[pix_id] = last_contributor;
+	c->acc_final[pix_id] = acc;
+	c->D_final[pix_id] = D;
 	for (int ch = 0; ch < NCH; ch++) out_color[(size_t)ch * H * W + pix_id] = C[ch] + T * c->bg[ch];
 	out_depth[pix_id] = (acc > 0.5f) ? D / acc : 0.0f; /* forward.cu:464-468 */
 	*evaluated += ev;
@@ -544,6 +547,8 @@ int orc_forward(orc_ctx* c, const orc_inputs* in, float* out_color, float* out_d
 	/* renderCUDA (forward.cu:341-471) */
 	c->final_T = (float*)calloc(npix ? npix : 1, sizeof(float));
 	c->n_contrib = (uint32_t*)calloc(npix ? npix : 1, sizeof(uint32_t));
+	c->acc_final = (float*)calloc(npix ? npix : 1, sizeof(float));
+	c->D_final = (float*)calloc(npix ? npix : 1, sizeof(float));
 	const float* features = c->colors_precomp ? c->colors_precomp : c->rgb; /* rasterizer_impl.cu:322 */
 	long long ev_total = 0, co_total = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : ev_total, co_total)
@@ -598,9 +603,15 @@ static void atomic_addf(float* p, float v)
 }
 
 /* renderCUDA backward for one pixel (backward.cu:399-586). dL_dconic is [P][4] (x, y, -, w). */
+/* With dL_ddepths != NULL (EXTENSION, default off: the reference has every depth line commented out,
+ * backward.cu:443-554) the depth image also carries gradient.  The forward's depth is D/acc with
+ * D = sum T alpha z, acc = 1e-6 + sum T alpha, gated by acc > 0.5 (forward.cu:464-468), so D and acc
+ * enter the recurrence as two more blended channels (per-Gaussian values z and 1, no background term)
+ * with pixel gradients gD = g/acc and gA = -g D/acc^2, exactly like the dead code treats its depth
+ * channel (accum_depth_rec / last_depth), and z collects dL_dz = sum alpha T gD. */
 static void render_pixel_backward(const orc_ctx* c, int px, int py, uint32_t start, uint32_t end, const float* colors,
-                                  const float* dL_dpixels, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
-                                  float* dL_dcolors)
+                                  const float* dL_dpixels, const float* dL_ddepths, float* dL_dmean2D, float* dL_dconic,
+                                  float* dL_dopacity, float* dL_dcolors, float* dL_dz)
 {
 	const int W = c->W, H = c->H;
 	const uint32_t pix_id = (uint32_t)W * py + px;
@@ -612,6 +623,14 @@ static void render_pixel_backward(const orc_ctx* c, int px, int py, uint32_t sta
 	float accum_rec[NCH] = {0, 0, 0}, dL_dpixel[NCH], last_color[NCH] = {0, 0, 0};
 	for (int i = 0; i < NCH; i++) dL_dpixel[i] = dL_dpixels[(size_t)i * H * W + pix_id];
 	float last_alpha = 0;
+	float gD = 0, gA = 0, accum_depth_rec = 0, last_depth = 0, accum_one_rec = 0, last_one = 0;
+	if (dL_ddepths) {
+		const float acc = c->acc_final[pix_id];
+		if (acc > 0.5f) {
+			gD = dL_ddepths[pix_id] / acc;
+			gA = -dL_ddepths[pix_id] * c->D_final[pix_id] / (acc * acc);
+		}
+	}
 	const float ddelx_dx = (float)(0.5 * W), ddely_dy = (float)(0.5 * H); /* backward.cu:473-474 (double) */
 
 	for (uint32_t k = end; k-- > start;) {
@@ -636,6 +655,16 @@ static void render_pixel_backward(const orc_ctx* c, int px, int py, uint32_t sta
 			const float dL_dchannel = dL_dpixel[ch];
 			dL_dalpha += (col - accum_rec[ch]) * dL_dchannel;
 			atomic_addf(&dL_dcolors[id * NCH + ch], dchannel_dcolor * dL_dchannel);
+		}
+		if (dL_ddepths) {
+			const float c_d = c->depths[id];
+			accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
+			last_depth = c_d;
+			dL_dalpha += (c_d - accum_depth_rec) * gD;
+			accum_one_rec = last_alpha * last_one + (1.f - last_alpha) * accum_one_rec;
+			last_one = 1.f;
+			dL_dalpha += (1.f - accum_one_rec) * gA;
+			atomic_addf(&dL_dz[id], dchannel_dcolor * gD);
 		}
 		dL_dalpha *= T;
 		last_alpha = alpha;
@@ -832,7 +861,12 @@ static void cov3d_backward(const orc_ctx* c, int idx, const float* dL_dcov3Ds, f
 
 /* Rasterizer::backward (rasterizer_impl.cu:403-504) after orc_forward on the same ctx.
  * All gradient arrays are zero-filled here like rasterize_points.cu:154-162. dL_dout_depth is unused. */
-int orc_backward(orc_ctx* c, const float* dL_dpixels, const orc_grads* g)
+int orc_backward_ex(orc_ctx* c, const float* dL_dpixels, const float* dL_ddepths, const orc_grads* g);
+int orc_backward(orc_ctx* c, const float* dL_dpixels, const orc_grads* g) { return orc_backward_ex(c, dL_dpixels, NULL, g); }
+
+/* dL_ddepths == NULL: the reference's behaviour (depth carries no gradient).  Non-NULL: the opt-in
+ * depth-gradient extension described at render_pixel_backward. */
+int orc_backward_ex(orc_ctx* c, const float* dL_dpixels, const float* dL_ddepths, const orc_grads* g)
 {
 	const int P = c->P, M = c->M, W = c->W, H = c->H;
 	memset(g->dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P);
@@ -845,6 +879,7 @@ int orc_backward(orc_ctx* c, const float* dL_dpixels, const orc_grads* g)
 	memset(g->dL_drotations, 0, sizeof(float) * 4 * (size_t)P);
 	if (P == 0) return 0;
 	float* dL_dconic = (float*)calloc((size_t)4 * P, sizeof(float));
+	float* dL_dz = (float*)calloc((size_t)P, sizeof(float));
 	const float* colors = c->colors_precomp ? c->colors_precomp : c->rgb; /* rasterizer_impl.cu:453 */
 	const int ntiles = c->gx * c->gy;
 #pragma omp parallel for schedule(dynamic, 1)
@@ -856,8 +891,8 @@ int orc_backward(orc_ctx* c, const float* dL_dpixels, const orc_grads* g)
 			for (int lx = 0; lx < BLOCK_X; lx++) {
 				const int px = tx * BLOCK_X + lx, py = ty * BLOCK_Y + ly;
 				if (px < W && py < H)
-					render_pixel_backward(c, px, py, start, end, colors, dL_dpixels, g->dL_dmeans2D, dL_dconic,
-					                      g->dL_dopacity, g->dL_dcolors);
+					render_pixel_backward(c, px, py, start, end, colors, dL_dpixels, dL_ddepths, g->dL_dmeans2D, dL_dconic,
+					                      g->dL_dopacity, g->dL_dcolors, dL_dz);
 			}
 	}
 	const float* cov3D_all = c->cov3D_precomp ? c->cov3D_precomp : c->cov3D; /* rasterizer_impl.cu:481 */
@@ -877,9 +912,15 @@ int orc_backward(orc_ctx* c, const float* dL_dpixels, const orc_grads* g)
 		g->dL_dmeans3D[3 * idx] += (proj[0] * m_w - proj[3] * mul1) * d2x + (proj[1] * m_w - proj[3] * mul2) * d2y;
 		g->dL_dmeans3D[3 * idx + 1] += (proj[4] * m_w - proj[7] * mul1) * d2x + (proj[5] * m_w - proj[7] * mul2) * d2y;
 		g->dL_dmeans3D[3 * idx + 2] += (proj[8] * m_w - proj[11] * mul1) * d2x + (proj[9] * m_w - proj[11] * mul2) * d2y;
+		if (dL_ddepths) { /* z = p_view.z = view[2] x + view[6] y + view[10] z + view[14] (forward.cu:186,250) */
+			g->dL_dmeans3D[3 * idx] += c->view[2] * dL_dz[idx];
+			g->dL_dmeans3D[3 * idx + 1] += c->view[6] * dL_dz[idx];
+			g->dL_dmeans3D[3 * idx + 2] += c->view[10] * dL_dz[idx];
+		}
 		if (c->shs) sh_backward(c, idx, g->dL_dcolors, g->dL_dmeans3D, g->dL_dsh);
 		if (c->scales) cov3d_backward(c, idx, g->dL_dcov3D, g->dL_dscales, g->dL_drotations);
 	}
 	free(dL_dconic);
+	free(dL_dz);
 	return 0;
 }

@@ -50,6 +50,16 @@ class OracleBackend:
         return (t("dL_dmeans2D"), t("dL_dcolors"), t("dL_dopacity"), t("dL_dmeans3D"), t("dL_dcov3D"), t("dL_dsh"),
                 t("dL_dscales"), t("dL_drotations"))
 
+    def rasterize_gaussians_backward_depth(self, bg, means3D, radii, colors, scales, rotations, scale_modifier,
+                                           cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                                           dL_dout_depth, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer,
+                                           debug, out_depth):
+        o = self._live.pop(int(geomBuffer[0].item()))
+        g = o.backward(_np(dL_dout_color), _np(dL_dout_depth))
+        t = lambda k: torch.from_numpy(g[k])
+        return (t("dL_dmeans2D"), t("dL_dcolors"), t("dL_dopacity"), t("dL_dmeans3D"), t("dL_dcov3D"), t("dL_dsh"),
+                t("dL_dscales"), t("dL_drotations"))
+
     def rasterize_aussians_filter(self, means3D, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                                   projmatrix, tan_fovx, tan_fovy, image_height, image_width, prefiltered, debug):
         o = orc.Oracle(self.threads)

@@ -337,3 +337,62 @@ def test_render_views_multi_stream_is_bit_identical_to_single_calls():
                                                  shs=scene.shs, scales=scene.scales, rotations=scene.rotations)
             assert torch.equal(c, color[k]) and torch.equal(d, depth[k]) and torch.equal(r, radii[k])
     assert (radii[0] > 0).sum() > 100
+
+
+@pytest.mark.parametrize("color", ["sh2", "precomp"])
+def test_opt_in_depth_gradient_vs_cpu_oracle(color):
+    """Extension: with depth_gradient=True the depth image back-propagates through D / acc.
+    The CPU oracle implements the same extension (oracle/rasterizer_oracle.c, orc_backward_ex; its
+    derivative is pinned by finite differences in tests/test_host_api.py); default stays gradient-free."""
+    from oracle import oracle as orc
+
+    api = pl.ours()
+    W, H = 150, 100
+    scene_cpu = synthetic.make_scene(4000, "object", color, -3.4, seed=21)
+    cam_cpu = synthetic.orbit_camera(W, H, 0.5)
+    bg = torch.tensor([0.1, 0.3, 0.5])
+    Wc, Wd = synthetic.loss_weights(W, H)
+    o = orc.run_scene(scene_cpu, cam_cpu, bg)
+    ref = o["oracle"].backward(Wc.numpy(), Wd.numpy())
+    ref_depth_only = o["oracle"].backward(np.zeros_like(Wc.numpy()), Wd.numpy())
+    assert np.abs(ref_depth_only["dL_dmeans3D"]).sum() > 0
+
+    scene, cam = scene_cpu.to(DEV), cam_cpu.to(DEV)
+    Wc_d, Wd_d = Wc.to(DEV), Wd.to(DEV)
+    settings = synthetic.raster_settings(cam, scene.sh_degree, bg.to(DEV), api.GaussianRasterizationSettings)
+    names = ["means3D", "opacities", "scales", "rotations"] + (["shs"] if scene.shs is not None else ["colors_precomp"])
+    key = {"means3D": "dL_dmeans3D", "opacities": "dL_dopacity", "scales": "dL_dscales", "rotations": "dL_drotations",
+           "shs": "dL_dsh", "colors_precomp": "dL_dcolors", "means2D": "dL_dmeans2D"}
+
+    def run(depth_gradient, use_color=True, sink=False):
+        leaves = {n: getattr(scene, n).detach().clone().requires_grad_(True) for n in names}
+        m2 = torch.zeros_like(scene.means3D, requires_grad=True)
+        sinks = {n: torch.zeros_like(t) for n, t in leaves.items()} if sink else None
+        rast = api.GaussianRasterizer(settings, grad_sink=sinks, depth_gradient=depth_gradient)
+        color_img, _, depth_img = rast(means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"],
+                                       shs=leaves.get("shs"), colors_precomp=leaves.get("colors_precomp"),
+                                       scales=leaves["scales"], rotations=leaves["rotations"])
+        loss = (depth_img * Wd_d).sum() + ((color_img * Wc_d).sum() if use_color else 0.0)
+        loss.backward()
+        g = {n: (sinks[n] if sink else t.grad) for n, t in leaves.items()}
+        g["means2D"] = m2.grad
+        return g
+
+    got = run(True)
+    for n, t in got.items():
+        assert pl.rel_l2(t.cpu(), torch.from_numpy(ref[key[n]]).reshape(t.shape)) <= 1e-3, n
+    got = run(True, use_color=False)
+    for n, t in got.items():
+        r = torch.from_numpy(ref_depth_only[key[n]]).reshape(t.shape)
+        if r.abs().sum() > 0:
+            assert pl.rel_l2(t.cpu(), r) <= 1e-3, n
+        else:
+            assert not t.any(), n
+    sunk = run(True, sink=True)
+    plain = run(True)
+    for n in names:
+        assert pl.rel_l2(sunk[n], plain[n]) <= 1e-4, n
+    # default (reference behaviour): a depth-only loss moves nothing
+    off = run(False, use_color=False)
+    for n, t in off.items():
+        assert t is None or not t.any(), n

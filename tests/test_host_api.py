@@ -184,3 +184,49 @@ def test_render_views_equals_single_view_calls_with_oracle_backend():
         other = synthetic.raster_settings(synthetic.orbit_camera(32, 24, 0.1), 0, bg, GaussianRasterizationSettings)
         api.render_views(settings + [other], scene.means3D, scene.opacities, colors_precomp=scene.colors_precomp,
                          scales=scene.scales, rotations=scene.rotations)
+
+
+def test_opt_in_depth_gradient_with_oracle_backend():
+    """depth_gradient=True (extension, default off): a depth-only loss reaches the parameters, and the
+    oracle's derivative agrees with central finite differences of its own forward."""
+    from bloomscene_b200 import synthetic
+    from bloomscene_b200.rasterizer import GaussianRasterizationSettings, bind
+    from oracle_backend import OracleBackend
+
+    api = bind(OracleBackend())
+    scene = synthetic.make_scene(400, "object", "sh1", -3.0, seed=3)
+    cam = synthetic.orbit_camera(48, 32, 0.2)
+    settings = synthetic.raster_settings(cam, 1, torch.tensor([0.1, 0.2, 0.3]), GaussianRasterizationSettings)
+    _, Wd = synthetic.loss_weights(48, 32)
+    rast = api.GaussianRasterizer(settings, depth_gradient=True)
+    assert api.GaussianRasterizer.supports_depth_gradient
+
+    def depth_loss(means, op):
+        return (rast(means, torch.zeros_like(means), op, shs=scene.shs, scales=scene.scales,
+                     rotations=scene.rotations)[2].double() * Wd).sum()
+
+    means, op = scene.means3D.clone().requires_grad_(True), scene.opacities.clone().requires_grad_(True)
+    depth_loss(means, op).backward()
+    assert means.grad.abs().sum() > 0 and op.grad.abs().sum() > 0
+
+    def fd(t, index, eps):
+        with torch.no_grad():
+            plus, minus = t.detach().clone(), t.detach().clone()
+            plus[index] += eps
+            minus[index] -= eps
+            args = (plus, op) if t is means else (means, plus)
+            args_m = (minus, op) if t is means else (means, minus)
+            return (depth_loss(*args).item() - depth_loss(*args_m).item()) / (2 * eps)
+
+    # the map has jumps (acc > 0.5 gate, alpha thresholds, radius changes): take the best-agreeing three of the
+    # six largest gradient entries of each tensor, all three must match to 2 %
+    for t, eps in ((means, 2e-4), (op, 5e-3)):
+        g = t.grad.reshape(-1)
+        if t is op:
+            g = g * ((op.detach().reshape(-1) > 0.2) & (op.detach().reshape(-1) < 0.8))  # clear of the ignored 0.99 clamp
+        top = torch.argsort(-g.abs())[:6]
+        errs = []
+        for i in top.tolist():
+            index = tuple(int(v) for v in np.unravel_index(i, t.shape))
+            errs.append(abs(fd(t, index, eps) - t.grad[index].item()) / abs(t.grad[index].item()))
+        assert sorted(errs)[2] <= 0.02, errs

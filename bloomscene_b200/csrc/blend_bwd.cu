@@ -1,28 +1,33 @@
 // Backward alpha-blend for sm_100a  <- reference renderCUDA (cuda_rasterizer/backward.cu:399-586).
 //
-// Same tile / warp / pixel mapping and shared-memory staging as the forward kernel, replayed
-// back-to-front.  Differences from the reference that change cost, not results:
+// Same tile / warp / pixel mapping, packed fp32 arithmetic and shared-memory staging as the forward
+// kernel (blend_fwd.cu): 4 warps per 16x16 tile, an 8x8-pixel block per warp, TWO PIXELS PER LANE —
+// (x, y) and (x, y + 4) — replayed back-to-front.  Differences from the reference that change cost,
+// not results:
 //   * the tile starts at max(n_contrib) over its pixels and each warp skips records behind the
-//     max(n_contrib) of ITS 32 pixels (the reference walks them with a per-thread `continue`);
-//   * per-warp conservative culling with the records' alpha>=1/255 boxes (see blend_fwd.cu);
+//     max(n_contrib) of ITS 64 pixels (the reference walks them with a per-thread `continue`);
+//   * per-warp exact culling with the records' alpha>=1/255 ellipses (see blend_fwd.cu);
+//   * the per-pixel chain is branch-free: a pixel that does not take a record runs it with alpha := 0,
+//     which leaves T (T * rcp(1) == T), the behind-colour recurrence (fma(0, x, beta) == beta) and the
+//     staged weights (0) exactly as skipping would;
 //   * the per-Gaussian gradient sums are NOT reduced pair by pair.  All nine are fixed linear
 //     functions of two per-pixel scalars,
 //         w = G * dL_dalpha            u = alpha * T
 //         dL_dopacity = S(w)           dL_dcolor_c = S(u * dL_dpixel_c)
 //         dL_dmean2D, dL_dconic  <-  S(w dx), S(w dy), S(w dx dx), S(w dx dy), S(w dy dy)
-//     so the pixel loop only stores (w, u) of a contributing record into a warp-private staging
-//     slot (2 STS).  Every 8 staged records the warp "flushes": lane (r, q) takes record r and
-//     pixel row q of the warp's 8x4 block, forms the row's moment / colour sums from 4 LDS.128,
-//     the 4 rows are combined with an 8-shuffle transposing tree, and the record leaves as one
-//     red.global.add.v2.f32 per lane (+1 scalar) on a 48-byte accumulator row.  That is ~20
-//     instructions per contributing (warp, record) instead of ~60 for a 9-value warp reduction,
-//     against the reference's 9 x 32-lane atomics per pair (backward.cu:537,574-583);
+//     so the pixel loop only stores the lane's (w, u) pairs of a contributing record into a
+//     warp-private staging slot (2 STS.64).  Every 8 staged records the warp "flushes": lane (r, q)
+//     takes record r and pixel rows q and q + 4 of the warp's block — which sit side by side in the
+//     staged float2s, so the row sums of both run packed — the 4 lanes of a record are combined with
+//     an 8-shuffle transposing tree, and the record leaves as one red.global.add.v2.f32 per lane
+//     (+1) on a 48-byte accumulator row, against the reference's 9 x 32-lane atomics per pair
+//     (backward.cu:537,574-583);
 //   * constant factors (0.5*W, 0.5*H, -0.5) are applied once per Gaussian in the preprocess
 //     backward instead of once per pair.
 // Parity quirks kept: the alpha derivative ignores the min(0.99,.) clamp, T is recovered by
 // division from T_final (backward.cu:513-517), and depth carries no gradient (all uses commented
-// out in the reference, backward.cu:443-554).  The alpha tests use the forward's pinned arithmetic
-// so exactly the same pairs contribute.
+// out in the reference, backward.cu:443-554) unless the caller opts in (template DEPTH).  The alpha
+// tests use the forward's pinned arithmetic so exactly the same pairs contribute.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,11 +35,16 @@ namespace brs {
 
 namespace {
 
-constexpr int BLEND_THREADS = TILE_X * TILE_Y;
+constexpr int BLEND_THREADS = 128; // 4 warps x (8x8 pixels), two pixels per lane
 constexpr int BLEND_WARPS = BLEND_THREADS / 32;
-constexpr int BATCH = 256;
-constexpr int GROUP = 8;         // contributing records staged per warp between flushes (8 records x 4 rows = 32 lanes)
-constexpr int STAGE_STRIDE = 68; // floats per staged record: w[32] | u[32] | batch slot + 3 pad -> the flush's LDS.128 are conflict-free
+constexpr int BATCH = 128;
+constexpr int GROUP = 8; // contributing records staged per warp between flushes (8 records x 4 lanes = 32 lanes)
+// Staged record: W2[4 rows][8 float2 + pad] | U2[same] | batch slot.  A float2 holds the values of the
+// pixels (x, row) and (x, row + 4).  Row pitch 20 and record stride 176 (= 16 mod 32) make the flush's
+// LDS.128 (lane (r, q): record r, row q) conflict-free.
+constexpr int ROW_PITCH = 20;
+constexpr int PLANE = 4 * ROW_PITCH; // 80 floats
+constexpr int STAGE_STRIDE = 176;
 
 __device__ __forceinline__ float rcp_approx(float x)
 {
@@ -49,7 +59,7 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 }
 
 // Flush `cnt` (<= GROUP) staged records of this warp.  Lane (r = lane >> 2, q = lane & 3) owns
-// record r and the q-th row (8 pixels) of the warp's pixel block.
+// record r and the pixel rows q (lo halves) and q + 4 (hi halves) of the warp's 8x8 block.
 template <bool DEPTH>
 __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int cnt,
                                             const StagedRecord* __restrict__ rec, const uint32_t* __restrict__ s_id,
@@ -65,56 +75,67 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int
 		v[i] = 0.f;
 	uint32_t id = 0;
 	if (live) {
-		const uint32_t idx = (uint32_t)__float_as_int(stage[r * STAGE_STRIDE + 64]);
+		const float* srow = stage + r * STAGE_STRIDE;
+		const uint32_t idx = (uint32_t)__float_as_int(srow[2 * PLANE]);
 		const float2 g = *reinterpret_cast<const float2*>(&rec[idx].geo);
 		const float4 con = rec[idx].con;
 		id = s_id[idx];
-		const float4* st = reinterpret_cast<const float4*>(stage + r * STAGE_STRIDE + q * 8);
-		const float4 wa = st[0], wb = st[1], ua = st[8], ub = st[9];
-		const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-		const float u[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
-		const float dy = g.y - (byf + (float)q);
+		const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(srow + q * ROW_PITCH);
+		const ulonglong2* up = reinterpret_cast<const ulonglong2*>(srow + PLANE + q * ROW_PITCH);
+		f32x2 w[8], u[8];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const ulonglong2 a = wp[k], b = up[k];
+			w[2 * k] = a.x; w[2 * k + 1] = a.y;
+			u[2 * k] = b.x; u[2 * k + 1] = b.y;
+		}
+		const float dyA = g.y - (byf + (float)q), dyB = g.y - (byf + (float)(q + 4));
 		const float dx0 = g.x - bxf;
-		float S0 = 0.f, Sx = 0.f, Sxx = 0.f;
+		f32x2 S0 = bc2(0.f), Sx = bc2(0.f), Sxx = bc2(0.f);
 #pragma unroll
 		for (int i = 0; i < 8; i++) {
-			const float dx = dx0 - (float)i;
-			const float t = w[i] * dx;
-			S0 += w[i];
-			Sx += t;
-			Sxx = fmaf(t, dx, Sxx);
+			const f32x2 dx = bc2(dx0 - (float)i);
+			const f32x2 t = mul2(w[i], dx);
+			S0 = add2(S0, w[i]);
+			Sx = add2(Sx, t);
+			Sxx = fma2(t, dx, Sxx);
 		}
-		const float4* dp = reinterpret_cast<const float4*>(s_dpx + q * 8);
-		constexpr int NCH = DEPTH ? 4 : 3; // with DEPTH the 4th row of s_dpx holds gD = dL_dD
+		constexpr int NCH = DEPTH ? 4 : 3; // with DEPTH the 4th plane of s_dpx holds gD = dL_dD
 		float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
 		for (int ch = 0; ch < NCH; ch++) {
-			const float4 da = dp[ch * 8], db = dp[ch * 8 + 1];
-			float s = u[0] * da.x;
-			s = fmaf(u[1], da.y, s);
-			s = fmaf(u[2], da.z, s);
-			s = fmaf(u[3], da.w, s);
-			s = fmaf(u[4], db.x, s);
-			s = fmaf(u[5], db.y, s);
-			s = fmaf(u[6], db.z, s);
-			s = fmaf(u[7], db.w, s);
-			c[ch] = s;
+			const ulonglong2* dp = reinterpret_cast<const ulonglong2*>(s_dpx + ch * PLANE + q * ROW_PITCH);
+			const ulonglong2 d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3];
+			f32x2 s = mul2(u[0], d0.x);
+			s = fma2(u[1], d0.y, s);
+			s = fma2(u[2], d1.x, s);
+			s = fma2(u[3], d1.y, s);
+			s = fma2(u[4], d2.x, s);
+			s = fma2(u[5], d2.y, s);
+			s = fma2(u[6], d3.x, s);
+			s = fma2(u[7], d3.y, s);
+			c[ch] = lo2(s) + hi2(s);
 		}
-		const float Sy = dy * S0, Sxy = dy * Sx, Syy = dy * Sy;
+		const float S0a = lo2(S0), S0b = hi2(S0), Sxa = lo2(Sx), Sxb = hi2(Sx);
+		const float S0t = S0a + S0b, Sxt = Sxa + Sxb, Sxxt = lo2(Sxx) + hi2(Sxx);
+		const float Sya = dyA * S0a, Syb = dyB * S0b;
+		const float Sy = Sya + Syb;
+		const float Sxy = fmaf(dyA, Sxa, dyB * Sxb);
+		const float Syy = fmaf(dyA, Sya, dyB * Syb);
 		const float o = con.w;
 		// dL_dG * G = o * w;  dG_ddelx = -G (dx a + dy b),  dG_ddely = -G (dy c + dx b)
-		v[0] = -o * (con.x * Sx + con.y * Sy); // x 0.5*W later
-		v[1] = -o * (con.z * Sy + con.y * Sx); // x 0.5*H later
-		v[2] = o * Sxx;                         // x -0.5 later
+		v[0] = -o * (con.x * Sxt + con.y * Sy); // x 0.5*W later
+		v[1] = -o * (con.z * Sy + con.y * Sxt); // x 0.5*H later
+		v[2] = o * Sxxt;                         // x -0.5 later
 		v[3] = o * Sxy;
 		v[4] = o * Syy;
-		v[5] = S0;
+		v[5] = S0t;
 		v[6] = c[0];
 		v[7] = c[1];
 		v[8] = c[2];
 		v[9] = c[3];
 	}
-	// combine the 4 rows (lanes q = 0..3 of a record): 9 -> 5 -> 3 values per lane, 8 shuffles.
+	// combine the 4 lanes of a record (q = 0..3): 9 -> 5 -> 3 values per lane, 8 shuffles.
 	// Afterwards lane q holds slots 2q, 2q + 1 in (a, b) and every lane holds slot 8 in c8.
 	const bool h2 = lane & 2, h1 = lane & 1;
 	float r4[4];
@@ -168,52 +189,71 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 	__shared__ StagedRecord s_rec[2][BATCH];
 	__shared__ uint32_t s_ids[2][BATCH];
 	__shared__ __align__(16) float s_stage[BLEND_WARPS][GROUP * STAGE_STRIDE];
-	__shared__ __align__(16) float s_dpx[BLEND_WARPS][(DEPTH ? 4 : 3) * 32];
+	__shared__ __align__(16) float s_dpx[BLEND_WARPS][(DEPTH ? 4 : 3) * PLANE];
 	__shared__ uint32_t s_max[BLEND_WARPS];
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
-	const uint32_t bx = tile_x * TILE_X + (warp & 1) * 8;
-	const uint32_t by = tile_y * TILE_Y + (warp >> 1) * 4;
-	const uint32_t px = bx + (lane & 7), py = by + (lane >> 3);
-	const bool inside = px < (uint32_t)a.W && py < (uint32_t)a.H;
-	const uint32_t pix_id = (uint32_t)a.W * py + px;
-	const float pixfx = (float)px, pixfy = (float)py;
-	const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
+	const uint32_t bx = tile_x * TILE_X + (warp & 1) * 8; // this warp's 8x8 pixel block
+	const uint32_t by = tile_y * TILE_Y + (warp >> 1) * 8;
+	const uint32_t px = bx + (lane & 7), py0 = by + (lane >> 3), py1 = py0 + 4;
+	const bool inside0 = px < (uint32_t)a.W && py0 < (uint32_t)a.H;
+	const bool inside1 = px < (uint32_t)a.W && py1 < (uint32_t)a.H;
+	const uint32_t pix0 = (uint32_t)a.W * py0 + px, pix1 = (uint32_t)a.W * py1 + px;
+	const float pixfx = (float)px;
+	const f32x2 pixfy = pk2((float)py0, (float)py1);
+	const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 7);
 
 	const ExpConsts ek = {a.exp_c_scale, a.exp_c_252};
 	const uint2 range = __ldg(a.ranges + tile_y * a.grid_x + tile_x);
 
-	const float T_final = inside ? __ldg(a.final_T + pix_id) : 0.0f;
-	float T = T_final;
-	const int last_contributor = inside ? (int)__ldg(a.n_contrib + pix_id) : 0;
+	const float Tf0 = inside0 ? __ldg(a.final_T + pix0) : 0.0f, Tf1 = inside1 ? __ldg(a.final_T + pix1) : 0.0f;
+	F2 T = {Tf0, Tf1};
+	const int last0 = inside0 ? (int)__ldg(a.n_contrib + pix0) : 0, last1 = inside1 ? (int)__ldg(a.n_contrib + pix1) : 0;
 
-	float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f;
-	if (inside) {
-		const size_t plane = (size_t)a.W * a.H;
-		dpx0 = __ldg(a.dL_dpixels + pix_id);
-		dpx1 = __ldg(a.dL_dpixels + plane + pix_id);
-		dpx2 = __ldg(a.dL_dpixels + 2 * plane + pix_id);
+	// per-pixel upstream gradients; the flush reads them from shared memory as (row, row + 4) pairs
+	const size_t plane = (size_t)a.W * a.H;
+	float2 d0 = {0.f, 0.f}, d1 = d0, d2 = d0;
+	if (inside0) {
+		d0.x = __ldg(a.dL_dpixels + pix0);
+		d1.x = __ldg(a.dL_dpixels + plane + pix0);
+		d2.x = __ldg(a.dL_dpixels + 2 * plane + pix0);
 	}
-	s_dpx[warp][lane] = dpx0;
-	s_dpx[warp][32 + lane] = dpx1;
-	s_dpx[warp][64 + lane] = dpx2;
-	float gD = 0.f, gA = 0.f;
+	if (inside1) {
+		d0.y = __ldg(a.dL_dpixels + pix1);
+		d1.y = __ldg(a.dL_dpixels + plane + pix1);
+		d2.y = __ldg(a.dL_dpixels + 2 * plane + pix1);
+	}
+	const uint32_t pair_off = (lane >> 3) * ROW_PITCH + (lane & 7) * 2; // this lane's float2 inside a plane
+	float* const dpx_rows = s_dpx[warp];
+	*reinterpret_cast<float2*>(dpx_rows + pair_off) = d0;
+	*reinterpret_cast<float2*>(dpx_rows + PLANE + pair_off) = d1;
+	*reinterpret_cast<float2*>(dpx_rows + 2 * PLANE + pair_off) = d2;
+	float2 gD = {0.f, 0.f}, gA = {0.f, 0.f};
 	if (DEPTH) {
-		if (inside) {
-			const float depth = __ldg(a.out_depth + pix_id);
+		if (inside0) {
+			const float depth = __ldg(a.out_depth + pix0);
 			if (depth > 0.f) { // the forward's acc > 0.5 gate (view-space z > 0.2, so D / acc > 0 exactly when it passed)
-				const float acc = 0.000001f + (1.0f - T_final);
-				const float g_over_acc = __fdividef(__ldg(a.dL_ddepth + pix_id), acc);
-				gD = g_over_acc;
-				gA = -g_over_acc * depth;
+				const float g_over_acc = __fdividef(__ldg(a.dL_ddepth + pix0), 0.000001f + (1.0f - Tf0));
+				gD.x = g_over_acc;
+				gA.x = -g_over_acc * depth;
 			}
 		}
-		s_dpx[warp][96 + lane] = gD;
+		if (inside1) {
+			const float depth = __ldg(a.out_depth + pix1);
+			if (depth > 0.f) {
+				const float g_over_acc = __fdividef(__ldg(a.dL_ddepth + pix1), 0.000001f + (1.0f - Tf1));
+				gD.y = g_over_acc;
+				gA.y = -g_over_acc * depth;
+			}
+		}
+		*reinterpret_cast<float2*>(dpx_rows + 3 * PLANE + pair_off) = gD;
 	}
+	const f32x2 dpx0 = pk2(d0.x, d0.y), dpx1 = pk2(d1.x, d1.y), dpx2 = pk2(d2.x, d2.y);
+	const f32x2 gD2 = pk2(gD.x, gD.y), gA2 = pk2(gA.x, gA.y);
 
 	// records at list positions >= max(n_contrib) are skipped by every pixel of the warp / tile
-	int warp_max = last_contributor;
+	int warp_max = max(last0, last1);
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1)
 		warp_max = max(warp_max, __shfl_xor_sync(0xffffffffu, warp_max, o));
@@ -226,17 +266,16 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 		tile_max = max(tile_max, (int)s_max[w]);
 	const int n = min((int)(range.y - range.x), tile_max);
 
-	float beta = 0.f, last_alpha = 0.f, last_cd = 0.f;
-	float bg_dot_dpixel = 0.f;
-	bg_dot_dpixel += __ldg(a.bg + 0) * dpx0;
-	bg_dot_dpixel += __ldg(a.bg + 1) * dpx1;
-	bg_dot_dpixel += __ldg(a.bg + 2) * dpx2;
-	const float neg_Tf_bg = -T_final * bg_dot_dpixel;
+	F2 beta = {0.f, 0.f}, last_alpha = {0.f, 0.f}, last_cd = {0.f, 0.f};
+	const float bg0 = __ldg(a.bg + 0), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
+	float bgd0 = 0.f, bgd1 = 0.f;
+	bgd0 += bg0 * d0.x; bgd0 += bg1 * d1.x; bgd0 += bg2 * d2.x;
+	bgd1 += bg0 * d0.y; bgd1 += bg1 * d1.y; bgd1 += bg2 * d2.y;
+	const f32x2 neg_Tf_bg = pk2(-Tf0 * bgd0, -Tf1 * bgd1);
 
 	float* const stage = s_stage[warp];
-	const float* const dpx_rows = s_dpx[warp];
 	int staged = 0;
-	float* st = stage + lane; // this lane's column of the next free staging slot
+	float* st = stage + pair_off; // this lane's float2 in the W2 plane of the next free staging slot
 
 	// batches walk the list backwards: slot s of the batch at `base` holds list position n-1-(base+s).
 	// Double-buffered cp.async staging as in the forward: batch b+1 lands while batch b is processed.
@@ -260,9 +299,9 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 		const uint32_t* s_id = s_ids[buf];
 		const int cnt = min(BATCH, n - base);
 
-		// slot idx is list position n-1-base-idx; it is in front of this pixel's last contributor
+		// slot idx is list position n-1-base-idx; it is in front of a pixel's last contributor
 		// iff idx > first_live (and of this warp's iff idx > warp_first_live)
-		const int first_live = n - 1 - base - last_contributor;
+		const int first_live0 = n - 1 - base - last0, first_live1 = n - 1 - base - last1;
 		const int warp_first_live = n - 1 - base - warp_max;
 
 		for (int c0 = 0; c0 < cnt; c0 += 32) {
@@ -280,49 +319,61 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				const float2 g = *reinterpret_cast<const float2*>(&r->geo);
 				const float4 con = r->con;
 				const float dx = g.x - pixfx;
-				const float dy = g.y - pixfy;
-				const float t1 = __fmul_rn(dy, __fmul_rn(dy, con.z));
-				const float s = __fmaf_rn(dx, __fmul_rn(dx, con.x), t1);
-				const float t3 = __fmul_rn(dy, __fmul_rn(dx, con.y));
-				const float power = __fmaf_rn(s, -0.5f, -t3);
-				const float G = expf_exact(power, ek);
-				const float alpha = fminf(0.99f, __fmul_rn(con.w, G));
-				const bool ok = (idx > first_live) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-				if (!__any_sync(0xffffffffu, ok))
+				const float dxa = __fmul_rn(dx, con.x);
+				const float dxb = __fmul_rn(dx, con.y);
+				const f32x2 ndy = sub2(pixfy, bc2(g.y)); // -(dy): see blend_fwd.cu
+				const f32x2 t1 = mul2(ndy, mul2(ndy, bc2(con.z)));
+				const f32x2 s = fma2(bc2(dx), bc2(dxa), t1);
+				const f32x2 nt3 = mul2(ndy, bc2(dxb));
+				const f32x2 power = fma2(s, bc2(-0.5f), nt3);
+				const f32x2 G = expf_exact2(power, ek);
+				const f32x2 oG = mul2(bc2(con.w), G);
+				const float alpha0 = fminf(0.99f, lo2(oG)), alpha1 = fminf(0.99f, hi2(oG));
+				const bool ok0 = (idx > first_live0) && !(lo2(power) > 0.0f) && !(alpha0 < 1.0f / 255.0f);
+				const bool ok1 = (idx > first_live1) && !(hi2(power) > 0.0f) && !(alpha1 < 1.0f / 255.0f);
+				if (!__any_sync(0xffffffffu, ok0 || ok1))
 					continue;
 
 				const float4 col = r->col;
-				float w_ = 0.f, u_ = 0.f;
-				if (ok) {
-					// 1 - alpha >= 0.01 (alpha is clamped to 0.99): one MUFU.RCP (<= 1 ulp) replaces the
-					// reference's two IEEE divisions; gradients are tolerance-checked (rel-L2 <= 1e-4)
-					const float rcp = rcp_approx(1.f - alpha);
-					T = T * rcp;
-					u_ = alpha * T; // dchannel_dcolor
+				// a pixel that skips the record runs the chain with alpha = 0 (see the header)
+				const f32x2 al = pk2(ok0 ? alpha0 : 0.f, ok1 ? alpha1 : 0.f);
+				// 1 - alpha >= 0.01 (alpha is clamped to 0.99): one MUFU.RCP (<= 1 ulp, exact for 1.0) replaces the
+				// reference's two IEEE divisions; gradients are tolerance-checked (rel-L2 <= 1e-4)
+				const f32x2 om = sub2(bc2(1.0f), al);
+				const f32x2 rcp = pk2(rcp_approx(lo2(om)), rcp_approx(hi2(om)));
+				const f32x2 Tn = mul2(pk2(T), rcp);
+				const f32x2 u_ = mul2(al, Tn); // dchannel_dcolor
 
-					// reference backward.cu:519-533 keeps, per channel, the colour accumulated BEHIND this record
-					// (accum_rec) and sums (c - accum_rec) * dL_dpixel over the channels.  Only that sum is
-					// needed, so the recurrence runs on its projection: beta = accum_rec . dL_dpixel and
-					// cd = colour . dL_dpixel are scalars.
-					beta = fmaf(last_alpha, last_cd - beta, beta);
-					float cd = fmaf(col.z, dpx2, fmaf(col.y, dpx1, col.x * dpx0));
-					if (DEPTH)
-						cd = fmaf(col.w, gD, cd) + gA;
-					float dL_dalpha = (cd - beta) * T;
-					last_cd = cd;
-					last_alpha = alpha;
-					dL_dalpha += neg_Tf_bg * rcp;
-					w_ = G * dL_dalpha;
-				}
-				st[0] = w_;
-				st[32] = u_;
+				// reference backward.cu:519-533 keeps, per channel, the colour accumulated BEHIND this record
+				// (accum_rec) and sums (c - accum_rec) * dL_dpixel over the channels.  Only that sum is
+				// needed, so the recurrence runs on its projection: beta = accum_rec . dL_dpixel and
+				// cd = colour . dL_dpixel are scalars.
+				const f32x2 b_old = pk2(beta);
+				const f32x2 bn = fma2(pk2(last_alpha), sub2(pk2(last_cd), b_old), b_old);
+				f32x2 cd = fma2(bc2(col.z), dpx2, fma2(bc2(col.y), dpx1, mul2(bc2(col.x), dpx0)));
+				if (DEPTH)
+					cd = add2(fma2(bc2(col.w), gD2, cd), gA2);
+				f32x2 dL_dalpha = mul2(sub2(cd, bn), Tn);
+				dL_dalpha = fma2(neg_Tf_bg, rcp, dL_dalpha);
+				const f32x2 wv = mul2(G, dL_dalpha);
+				T = unpk2(Tn);
+				beta = unpk2(bn);
+				last_cd = unpk2(cd);
+				last_alpha = unpk2(al);
+				float2 w2, u2;
+				w2.x = ok0 ? lo2(wv) : 0.f;
+				w2.y = ok1 ? hi2(wv) : 0.f;
+				u2.x = lo2(u_);
+				u2.y = hi2(u_);
+				*reinterpret_cast<float2*>(st) = w2;
+				*reinterpret_cast<float2*>(st + PLANE) = u2;
 				if (lane == 0)
-					st[64] = __int_as_float(idx); // the record's batch slot rides in the row's padding
+					stage[staged * STAGE_STRIDE + 2 * PLANE] = __int_as_float(idx); // the record's batch slot
 				st += STAGE_STRIDE;
 				if (++staged == GROUP) {
 					flush_group<DEPTH>(stage, GROUP, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 					staged = 0;
-					st = stage + lane;
+					st = stage + pair_off;
 				}
 			}
 		}
@@ -330,7 +381,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 		if (staged) {
 			flush_group<DEPTH>(stage, staged, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 			staged = 0;
-			st = stage + lane;
+			st = stage + pair_off;
 		}
 	}
 }

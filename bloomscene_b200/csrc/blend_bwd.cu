@@ -39,12 +39,16 @@ constexpr int BLEND_THREADS = 128; // 4 warps x (8x8 pixels), two pixels per lan
 constexpr int BLEND_WARPS = BLEND_THREADS / 32;
 constexpr int BATCH = 128;
 constexpr int GROUP = 8; // contributing records staged per warp between flushes (8 records x 4 lanes = 32 lanes)
-// Staged record: W2[4 rows][8 float2 + pad] | U2[same] | batch slot.  A float2 holds the values of the
-// pixels (x, row) and (x, row + 4).  Row pitch 20 and record stride 176 (= 16 mod 32) make the flush's
-// LDS.128 (lane (r, q): record r, row q) conflict-free.
+// Staged record: W2 rows | U2 rows | batch slot, a row = 8 float2, a float2 = the values of the pixels
+// (x, row) and (x, row + 4).  Rows sit at float offsets {0, 16, 36, 52} (U2: + 72) and records 168 apart
+// (= 8 mod 32): the pixel loop's STS.64 (half-warp = two rows) and the flush's LDS.128 (lane (r, q):
+// record r, row q) are both bank-conflict-free.  s_dpx keeps planes of 4 rows x (8 float2 + 4 pad).
+__device__ __forceinline__ constexpr int stage_row(int row) { return row * 16 + (row >> 1) * 4; }
+constexpr int STAGE_U = 72;
+constexpr int STAGE_SLOT = 140;
+constexpr int STAGE_STRIDE = 168;
 constexpr int ROW_PITCH = 20;
 constexpr int PLANE = 4 * ROW_PITCH; // 80 floats
-constexpr int STAGE_STRIDE = 176;
 
 __device__ __forceinline__ float rcp_approx(float x)
 {
@@ -76,12 +80,12 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int
 	uint32_t id = 0;
 	if (live) {
 		const float* srow = stage + r * STAGE_STRIDE;
-		const uint32_t idx = (uint32_t)__float_as_int(srow[2 * PLANE]);
+		const uint32_t idx = (uint32_t)__float_as_int(srow[STAGE_SLOT]);
 		const float2 g = *reinterpret_cast<const float2*>(&rec[idx].geo);
 		const float4 con = rec[idx].con;
 		id = s_id[idx];
-		const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(srow + q * ROW_PITCH);
-		const ulonglong2* up = reinterpret_cast<const ulonglong2*>(srow + PLANE + q * ROW_PITCH);
+		const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(srow + stage_row(q));
+		const ulonglong2* up = reinterpret_cast<const ulonglong2*>(srow + STAGE_U + stage_row(q));
 		f32x2 w[8], u[8];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
@@ -275,7 +279,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 
 	float* const stage = s_stage[warp];
 	int staged = 0;
-	float* st = stage + pair_off; // this lane's float2 in the W2 plane of the next free staging slot
+	const uint32_t stage_off = stage_row(lane >> 3) + (lane & 7) * 2;
+	float* st = stage + stage_off; // this lane's W2 float2 in the next free staging slot
 
 	// batches walk the list backwards: slot s of the batch at `base` holds list position n-1-(base+s).
 	// Double-buffered cp.async staging as in the forward: batch b+1 lands while batch b is processed.
@@ -366,14 +371,14 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				u2.x = lo2(u_);
 				u2.y = hi2(u_);
 				*reinterpret_cast<float2*>(st) = w2;
-				*reinterpret_cast<float2*>(st + PLANE) = u2;
+				*reinterpret_cast<float2*>(st + STAGE_U) = u2;
 				if (lane == 0)
-					stage[staged * STAGE_STRIDE + 2 * PLANE] = __int_as_float(idx); // the record's batch slot
+					stage[staged * STAGE_STRIDE + STAGE_SLOT] = __int_as_float(idx); // the record's batch slot
 				st += STAGE_STRIDE;
 				if (++staged == GROUP) {
 					flush_group<DEPTH>(stage, GROUP, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 					staged = 0;
-					st = stage + pair_off;
+					st = stage + stage_off;
 				}
 			}
 		}
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 		if (staged) {
 			flush_group<DEPTH>(stage, staged, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);
 			staged = 0;
-			st = stage + pair_off;
+			st = stage + stage_off;
 		}
 	}
 }

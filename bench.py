@@ -46,8 +46,8 @@ N_VIEWS = 64
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch at config C, read from the
 # `ncu --set full` captures summarised under profiles/ (refreshed whenever a blend kernel changes).
 NCU_TRAFFIC = {
-    "blend_bwd": {"bytes": int((112.9 + 11.18) * 1e6), "source": "profiles/r01s6_ncu_full.md"},
-    "blend_fwd": {"bytes": int((76.45 + 27.05) * 1e6), "source": "profiles/r01s6_ncu_full.md"},
+    "blend_bwd": {"bytes": int((112.8 + 8.381) * 1e6), "source": "profiles/r01s7_ncu_full.md"},
+    "blend_fwd": {"bytes": int((76.46 + 23.93) * 1e6), "source": "profiles/r01s7_ncu_full.md"},
 }
 
 

@@ -25,4 +25,15 @@ for (P, color, W, H, mu) in [(3000, "sh3", 160, 96, -3.2), (1500, "precomp", 70,
     r = view_sharded_step(params, cams, bg, api.GaussianRasterizer, lambda c, d, vi: (c * Wc).sum() + (d * Wd).sum())
     torch.cuda.synchronize()
     print("step loss", float(r["loss"]))
+    # opt-in depth gradient (templated blend backward) and the forward-only batch entry point
+    settings = [synthetic.raster_settings(c, scene.sh_degree, bg, api.GaussianRasterizationSettings) for c in cams]
+    leaves = {n: getattr(scene, n).detach().clone().requires_grad_(True) for n in ("means3D", "opacities", "scales", "rotations")}
+    col = {"shs": scene.shs} if scene.shs is not None else {"colors_precomp": scene.colors_precomp}
+    rast = api.GaussianRasterizer(settings[0], depth_gradient=True)
+    c_img, _, d_img = rast(means3D=leaves["means3D"], means2D=torch.zeros_like(scene.means3D, requires_grad=True),
+                           opacities=leaves["opacities"], scales=leaves["scales"], rotations=leaves["rotations"], **col)
+    ((c_img * Wc).sum() + (d_img * Wd).sum()).backward()
+    frames = api.render_views(settings, scene.means3D, scene.opacities, scales=scene.scales, rotations=scene.rotations, **col)
+    torch.cuda.synchronize()
+    print("depth-grad", float(leaves["means3D"].grad.abs().sum()), "frames", float(frames[0].sum()))
 print("done")

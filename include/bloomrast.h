@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BRS_VERSION 100 /* 0.1.0 */
+#define BRS_VERSION 101 /* 0.1.1: brs_grads gained depth_gradient / out_depth */
 
 typedef struct CUstream_st* brs_stream; /* == cudaStream_t */
 

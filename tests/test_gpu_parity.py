@@ -396,3 +396,30 @@ def test_opt_in_depth_gradient_vs_cpu_oracle(color):
     off = run(False, use_color=False)
     for n, t in off.items():
         assert t is None or not t.any(), n
+
+
+def test_fuzz_small_scenes_vs_reference_cuda():
+    """Seeded random sweep over sizes the fixed cases do not hit: odd / tiny / non-multiple-of-8 images (the blend
+    kernels give every lane the pixels (x, y) and (x, y + 4) of an 8x8 block), Gaussian sizes from sub-pixel to
+    screen-filling (saturation, 0.99 clamp), every colour mode, random background and scale modifier."""
+    _ref_or_skip()
+    rng = np.random.default_rng(20261017)
+    colors = ["sh0", "sh1", "sh2", "sh3", "sh1m16", "precomp"]
+    for i in range(28):
+        P = int(rng.integers(1, 4000))
+        W, H = (int(rng.integers(1, 12)), int(rng.integers(1, 12))) if i % 4 == 0 else (int(rng.integers(9, 150)), int(rng.integers(5, 110)))
+        kind = "band" if i % 5 == 4 else "object"
+        color = colors[i % len(colors)]
+        mu = float(rng.uniform(-4.2, -1.2))
+        bg = torch.tensor(rng.uniform(0, 1, 3), dtype=torch.float32, device=DEV)
+        mod = float(rng.uniform(0.5, 2.0))
+        scene = synthetic.make_scene(P, kind, color, mu, seed=1000 + i).to(DEV)
+        cam = (synthetic.orbit_camera(W, H, float(rng.uniform(0, 6.28))) if kind == "object"
+               else synthetic.yaw_camera(W, H, float(rng.uniform(0, 6.28)))).to(DEV)
+        tag = (i, P, W, H, kind, color, round(mu, 2), round(mod, 2))
+        try:
+            _assert_stage_parity(pl.compare_stages(scene, cam, bg, scale_modifier=mod))
+            Wc, Wd = (t.to(DEV) for t in synthetic.loss_weights(W, H, seed=i))
+            _assert_grad_parity(pl.compare_autograd(scene, cam, bg, Wc, Wd, scale_modifier=mod))
+        except AssertionError as e:
+            raise AssertionError(f"fuzz case {tag}: {e}") from e

@@ -39,14 +39,15 @@ constexpr int BLEND_THREADS = 128; // 4 warps x (8x8 pixels), two pixels per lan
 constexpr int BLEND_WARPS = BLEND_THREADS / 32;
 constexpr int BATCH = 128;
 constexpr int GROUP = 8; // contributing records staged per warp between flushes (8 records x 4 lanes = 32 lanes)
-// Staged record: W2 rows | U2 rows | batch slot, a row = 8 float2, a float2 = the values of the pixels
-// (x, row) and (x, row + 4).  Rows sit at float offsets {0, 16, 36, 52} (U2: + 72) and records 168 apart
-// (= 8 mod 32): the pixel loop's STS.64 (half-warp = two rows) and the flush's LDS.128 (lane (r, q):
-// record r, row q) are both bank-conflict-free.  s_dpx keeps planes of 4 rows x (8 float2 + 4 pad).
+// Staged record (136 floats): W2 rows | batch slot | U2 rows, a row = 8 float2, a float2 = the values of the
+// pixels (x, row) and (x, row + 4).  W2 rows sit at float offsets {0, 16, 36, 52}, the slot index in the gap at 32,
+// U2 rows at 68 + {0, 16, 36, 52}; records are 136 apart (= 8 mod 32): the pixel loop's STS.64 (half-warp = two
+// rows) and the flush's LDS.128 (lane (r, q): record r, row q) are both bank-conflict-free.  s_dpx keeps planes
+// of 4 rows x (8 float2 + 4 pad).
 __device__ __forceinline__ constexpr int stage_row(int row) { return row * 16 + (row >> 1) * 4; }
-constexpr int STAGE_U = 72;
-constexpr int STAGE_SLOT = 140;
-constexpr int STAGE_STRIDE = 168;
+constexpr int STAGE_U = 68;
+constexpr int STAGE_SLOT = 32;
+constexpr int STAGE_STRIDE = 136;
 constexpr int ROW_PITCH = 20;
 constexpr int PLANE = 4 * ROW_PITCH; // 80 floats
 

@@ -20,7 +20,8 @@ COLS = [
     ("gpu__time_duration.sum", "ms"),
     ("dram__bytes_read.sum", "dram rd MB"),
     ("dram__bytes_write.sum", "dram wr MB"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+    ("dram__bytes.sum.per_second", "dram GB/s"),
+    ("__dram_pct_of_measured_peak", "% of 6549 GB/s"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ %"),
@@ -48,6 +49,16 @@ def main():
         cells = []
         for key, _ in COLS:
             v = r[ix[key]] if key in ix else ""
+            if key == "__dram_pct_of_measured_peak" and "dram__bytes.sum.per_second" in ix:
+                try:
+                    bps = float(r[ix["dram__bytes.sum.per_second"]].replace(",", ""))
+                    un = units[ix["dram__bytes.sum.per_second"]]
+                    gbs = bps * {"byte/s": 1e-9, "Kbyte/s": 1e-6, "Mbyte/s": 1e-3, "Gbyte/s": 1.0, "Tbyte/s": 1e3}.get(un, 1.0)
+                    v = f"{100.0 * gbs / 6549.0:.1f}"
+                except ValueError:
+                    v = ""
+                cells.append(v)
+                continue
             if key == "Kernel Name":
                 v = v.split("(")[0].replace("brs::<unnamed>::", "").replace("void ", "")[:40]
             else:
@@ -56,6 +67,9 @@ def main():
                     u = units[ix[key]]
                     if key.startswith("dram__bytes"):
                         scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
+                        f *= scale
+                    if key == "dram__bytes.sum.per_second":
+                        scale = {"byte/s": 1e-9, "Kbyte/s": 1e-6, "Mbyte/s": 1e-3, "Gbyte/s": 1.0, "Tbyte/s": 1e3}.get(u, 1.0)
                         f *= scale
                     if key == "gpu__time_duration.sum":
                         scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1.0)

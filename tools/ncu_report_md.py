@@ -79,6 +79,27 @@ def main():
                     pass
             cells.append(v)
         lines.append("| " + " | ".join(cells) + " |")
+    # secondary metrics the north star asks for (pipes, shared memory, L2 reductions), % of peak
+    SEC = [("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe"),
+           ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe"),
+           ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU)"),
+           ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU"),
+           ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared-memory data pipe"),
+           ("lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed", "L2 reductions (RED)"),
+           ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots")]
+    picks = [r for r in rows[2:] if any(k in r[ix["Kernel Name"]] for k in ("blend_forward", "blend_backward", "preprocess_backward", "preprocess_kernel"))]
+    if picks:
+        lines += ["", "## Pipe / shared-memory / atomic utilisation (% of peak)", "",
+                  "| kernel | " + " | ".join(n for _, n in SEC) + " |", "|" + "---|" * (len(SEC) + 1)]
+        for r in picks:
+            name = r[ix["Kernel Name"]].split("(")[0].replace("brs::<unnamed>::", "").replace("void ", "")[:40]
+            vals = []
+            for key, _ in SEC:
+                try:
+                    vals.append(f"{float(r[ix[key]].replace(',', '')):.1f}")
+                except (KeyError, ValueError):
+                    vals.append("")
+            lines.append("| " + name + " | " + " | ".join(vals) + " |")
     for rx in regexes:
         src = run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{rx}"])
         if "Address" not in src:

@@ -99,19 +99,149 @@ def measured_peaks():
     return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
-def get_api(impl: str):
-    from bloomscene_b200.rasterizer import bind
+def get_api():
+    import bloomscene_b200
 
-    if impl == "ours":
-        import bloomscene_b200
+    return bloomscene_b200._api
 
-        return bloomscene_b200._api
+
+def make_config(cfg, views, world):
+    """The workload description both arms print (identical for the product and the reference arm)."""
+    W, H = cfg["W"], cfg["H"]
+    return {"workload": f"config E of BASELINE.md: {cfg['P']} Gaussians SH degree 3 (M=16), {W}x{H}, {views}-view "
+                        f"orbit batch, fwd+loss+bwd per view, view-sharded over {world} rank(s)"
+                        + (" + NCCL allreduce of the 236 MB gradient bucket" if world > 1 else ""),
+            "P": cfg["P"], "views": views, "resolution": [W, H], "sh_degree": 3,
+            "l2": "inputs larger than L2 (236 MB of parameters re-read per view, ~0.5 GB working set vs 126 MB L2)",
+            "parallelism": f"view-sharded dp{world}"}
+
+
+def kernel_census(fn):
+    """Names and counts of the CUDA kernels `fn()` launches (torch profiler / CUPTI, outside any timed region)."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = {}
+        for ev in prof.events():
+            if getattr(ev, "device_type", None) is not None and "cuda" in str(ev.device_type).lower():
+                n = ev.name.split("(")[0].split("<")[0]
+                if n.lower().startswith("memcpy") or n.lower().startswith("memset"):
+                    continue
+                names[n] = names.get(n, 0) + 1
+        return names
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": str(e)[:200]}
+
+
+def reference_arm(a):
+    """bench.py --impl reference: the reference's OWN rasterizer through the reference's OWN Python
+    package and stock code path — GaussianRasterizationSettings / GaussianRasterizer exactly as
+    gaussian_renderer/__init__.py:211-262 uses them, one view after the other on the current stream,
+    plain autograd accumulation into the parameters' .grad.  This function imports nothing of the
+    product: no bloomscene_b200 module, no libbloomrast.so, no product kernel.  The reference has no
+    CPU implementation of this path (its only implementation is CUDA), so the arm runs on ONE B200
+    whatever --gpus says; ranks other than 0 exit without work."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
     from oracle import build_ref
+    from workload import synthetic
+    from workload.params import GaussianParams
 
-    mod = build_ref.load()
-    if mod is None:
-        return None
-    return bind(mod)
+    ref = build_ref.load_reference_package()
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference CUDA rasterizer + its Python package) is not "
+                          "built; it needs /root/reference at build time"}))
+        return
+    assert "bloomscene_b200" not in sys.modules, "the reference arm must not load the product"
+    assert torch.cuda.is_available(), "the reference's only implementation of this path is CUDA"
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = synthetic.CONFIGS[CONFIG_NAME]
+    W, H = cfg["W"], cfg["H"]
+    config = make_config(cfg, a.views, 1)
+
+    scene_cpu = synthetic.config_scene(CONFIG_NAME)
+    cams_cpu = synthetic.config_cameras(CONFIG_NAME, a.views)
+    Wc_cpu, Wd_cpu = synthetic.loss_weights(W, H)
+    params = GaussianParams(scene_cpu.to(dev))
+    cams = [c.to(dev) for c in cams_cpu]
+    Wc_flat, Wd_flat = Wc_cpu.to(dev).reshape(-1), Wd_cpu.to(dev).reshape(-1)
+    bg = torch.zeros(3, device=dev)
+    t = params.tensors
+
+    def one_view(cam):
+        settings = synthetic.raster_settings(cam, params.sh_degree, bg, ref.GaussianRasterizationSettings)
+        rast = ref.GaussianRasterizer(raster_settings=settings)
+        means2D = torch.zeros_like(t["means3D"], requires_grad=True)  # gaussian_renderer/__init__.py:224-229
+        color, radii, depth = rast(means3D=t["means3D"], means2D=means2D, opacities=t["opacities"], shs=t["shs"],
+                                   colors_precomp=None, scales=t["scales"], rotations=t["rotations"], cov3D_precomp=None)
+        loss = torch.dot(color.reshape(-1), Wc_flat) + torch.dot(depth.reshape(-1), Wd_flat)
+        loss.backward()
+        return loss.detach()
+
+    def step():
+        params.zero_grad()
+        total = torch.zeros((), device=dev)
+        for cam in cams:
+            total += one_view(cam)
+        return total
+
+    host_params = torch.empty_like(params.flat, device="cpu").pin_memory()
+    host_params.copy_(params.flat)
+    host_grads = torch.empty_like(params.flat, device="cpu").pin_memory()
+    host_loss = torch.zeros(1).pin_memory()
+    cam_host = torch.stack([torch.cat([c.viewmatrix.flatten(), c.projmatrix.flatten(), c.campos]) for c in cams_cpu]).pin_memory()
+    cam_dev = torch.empty_like(cam_host, device=dev)
+
+    def step_e2e():
+        with torch.no_grad():
+            params.flat.copy_(host_params, non_blocking=True)
+            cam_dev.copy_(cam_host, non_blocking=True)
+        total = step()
+        host_grads.copy_(params.grad_bucket, non_blocking=True)
+        host_loss.copy_(total.reshape(1), non_blocking=True)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_step = timed(step, a.steps)
+    step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    clocks = sampler.stop()
+    census = kernel_census(lambda: one_view(cams[0]))
+    per_view = sum(v for v in census.values() if isinstance(v, int))
+    assert "bloomscene_b200" not in sys.modules
+    out = {"impl": "reference", "metric": METRIC, "value": a.views / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1,
+           "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "ms_per_view": ms_step / a.views,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config, "clocks": clocks,
+           "e2e": {"value": a.views / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": host_params.numel() * 4 + cam_host.numel() * 4,
+                   "d2h_bytes_per_step": host_grads.numel() * 4 + 4, "ms_per_step": ms_e2e},
+           "loss": float(host_loss.item()),
+           "reference_kind": "the reference's own CUDA rasterizer (oracle/_ref/_ref_C.so: unmodified sources built for sm_100a) "
+                             "through the reference's own Python package (oracle/_ref/pkg) on one B200; the reference has no CPU "
+                             "implementation of this path",
+           "cpu_baseline": {"value": a.views / (ms_step * 1e-3), "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                            "sample": f"all {a.views} views per step on one B200 (reference CUDA, not CPU)"},
+           "gpu_launches": per_view * a.views * a.steps, "kernels_per_view": census,
+           "product_modules_loaded": sorted(m for m in sys.modules if m.startswith("bloomscene_b200"))}
+    print(json.dumps(out))
 
 
 def stage_model(P, V, R, R1, M, npix, ntile, E, C, Eb):
@@ -158,20 +288,18 @@ def main():
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "cpu" else a.warmup
 
+    if a.impl == "reference":
+        return reference_arm(a)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    from bloomscene_b200 import synthetic
+    from workload import synthetic
 
     cfg = synthetic.CONFIGS[CONFIG_NAME]
     W, H = cfg["W"], cfg["H"]
-    config = {"workload": f"config E of BASELINE.md: {cfg['P']} Gaussians SH degree 3 (M=16), {W}x{H}, {a.views}-view "
-                          f"orbit batch, fwd+loss+bwd per view, view-sharded over {world} rank(s)"
-                          + (" + NCCL allreduce of the 236 MB gradient bucket" if world > 1 else ""),
-              "P": cfg["P"], "views": a.views, "resolution": [W, H], "sh_degree": 3,
-              "l2": "inputs larger than L2 (236 MB of parameters re-read per view, ~0.5 GB working set vs 126 MB L2)",
-              "parallelism": f"view-sharded dp{world}", "streams_per_rank": a.streams if a.impl == "ours" else 1}
+    config = make_config(cfg, a.views, world)
 
     # ---- CPU port as its own arm -------------------------------------------------------------------
     if a.impl == "cpu":
@@ -191,13 +319,7 @@ def main():
                           "gpu_launches": 0}))
         return
 
-    # ---- reference arm: rank 0 alone, one GPU ------------------------------------------------------
-    if a.impl == "reference" and rank != 0:
-        return
-    if a.impl == "reference":
-        world_eff, rank_eff = 1, 0
-    else:
-        world_eff, rank_eff = world, rank
+    world_eff, rank_eff = world, rank
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
@@ -207,12 +329,10 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    api = get_api(a.impl)
-    if api is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/_ref_C.so is not built (needs /root/reference at build time)"}))
-        return
+    api = get_api()
 
-    from bloomscene_b200.multiview import GaussianParams, download_grads, upload_params, view_sharded_step
+    from bloomscene_b200.multiview import download_grads, upload_params, view_sharded_step
+    from workload.params import GaussianParams
 
     scene_cpu = synthetic.config_scene(CONFIG_NAME)
     cams_cpu = synthetic.config_cameras(CONFIG_NAME, a.views)
@@ -289,7 +409,7 @@ def main():
 
     for _ in range(a.warmup):
         step()
-    count_launches = a.impl == "ours"
+    count_launches = True
     if count_launches:
         api._C.launch_count(True)
     sampler = ClockSampler(local_rank)
@@ -302,6 +422,32 @@ def main():
     ms_e2e = timed(step_e2e, a.steps)
     clocks = sampler.stop() if rank_eff == 0 else None
     loss_value = float(host_loss.item())
+
+    # ---- gradient parity of the step, outside the timed region -----------------------
+    # The bucket the step produced (views dealt over ranks and streams, in-kernel accumulation, NCCL
+    # allreduce when N > 1) against the same 64-view sum computed on rank 0 alone the plain way: one
+    # stream, fresh gradient tensors per view, autograd's own accumulation.  Bar: relative L2 <= 1e-4.
+    step()
+    torch.cuda.synchronize()
+    grad_parity = None
+    if rank_eff == 0:
+        got = params.grad_bucket.clone()
+
+        class PlainRasterizer(api.GaussianRasterizer):
+            supports_grad_sink = False
+
+        view_sharded_step(params, cams, bg, PlainRasterizer, loss_fn, rank=0, world=1, allreduce=False, streams=1)
+        torch.cuda.synchronize()
+        want = params.grad_bucket
+        grad_parity = {"rel_l2": float((got.double() - want.double()).norm() / want.double().norm())}
+        off = 0
+        for n in params.names:
+            sz = params.tensors[n].numel()
+            g, w = got[off:off + sz].double(), want[off:off + sz].double()
+            grad_parity[n] = float((g - w).norm() / w.norm())
+            off += sz
+        del got
+    barrier()
 
     if count_launches and world_eff > 1:
         import torch.distributed as dist
@@ -331,19 +477,16 @@ def main():
                         "link (slices exchanged over NVLink), bytes are whole-job totals; a step's device->host copy runs on a "
                         "copy stream and overlaps the next step's host->device copy (both inside the timed region)"},
         "loss": loss_value,
+        "grad_parity_rel_l2": None if grad_parity is None else grad_parity["rel_l2"],
+        "grad_parity": {"bar": 1e-4, "per_parameter": grad_parity,
+                        "what": "the step's (all-reduced) gradient bucket vs the same 64-view sum on rank 0 alone: one stream, "
+                                "fresh per-view gradient tensors, autograd accumulation"},
     }
-    if a.impl == "reference":
-        out["impl"] = "reference"
-        out["reference_kind"] = ("the reference's own CUDA rasterizer (oracle/_ref/_ref_C.so, unmodified sources, built for "
-                                 "sm_100a) on one B200 — the reference has no CPU implementation of this path")
-        out["cpu_baseline"] = {"value": out["value"], "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
-                               "sample": f"all {a.views} views per step on one B200 (reference CUDA, not CPU)"}
-        out["gpu_launches"] = None
-    else:
-        out["gpu_launches"] = launches
+    out["gpu_launches"] = launches
+    out["streams_per_rank"] = a.streams
 
     # ---- stage profile + roofline (ours, rank 0, outside the timed region) --------------------------
-    if a.impl == "ours" and rank_eff == 0:
+    if rank_eff == 0:
         from bloomscene_b200.profiling import profile_views
 
         prof = profile_views(api, params, cams, bg, Wc, rank_eff, world_eff, max_views=8)
@@ -382,16 +525,21 @@ def main():
                                    "not applicable); algorithmic flops = 21*E_b + 70*C with E_b, C counted by brs_count_pairs",
                            "hbm_peak_GBps": hbm_peak, "hbm_peak_source": hbm_src, "fp32_peak_TFLOPs": round(fp32_peak, 2),
                            "pipeline_frac": round(t_roof / sum(s["ms"] for s in stages.values()), 4),
+                           "pipeline_frac_serial": round(t_roof / sum(s["ms"] for s in stages.values()), 4),
+                           "pipeline_frac_overlapped": round(t_roof / (ms_step / len(range(rank_eff, a.views, world_eff))), 4),
+                           "pipeline_note": "stage times are measured with the views on ONE stream (serial sum); the step itself deals "
+                                            "the views of a rank onto several streams, so its ms per view is below that sum "
+                                            "(pipeline_frac_overlapped = roofline time / measured ms per view of this rank)",
                            "stages": stages, "per_view": st}
 
     # ---- CPU baseline (oracle port), N == 1 rank 0 only ----------------------------------------------
-    if a.impl == "ours" and world_eff == 1 and rank_eff == 0 and not a.no_cpu_baseline:
+    if world_eff == 1 and rank_eff == 0 and not a.no_cpu_baseline:
         n = max(1, min(a.cpu_views, a.views))
         vps, threads, dt = run_cpu_sample(scene_cpu, cams_cpu, Wc_cpu, n)
         out["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{n} of the {a.views} views of one step (forward+backward each) in {dt:.1f} s, "
                                          f"oracle/rasterizer_oracle.c with OpenMP on {threads} host threads"}
-    elif a.impl == "ours":
+    else:
         out["cpu_baseline"] = None
 
     if rank_eff == 0:

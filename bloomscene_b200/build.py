@@ -109,9 +109,27 @@ def build_ext(verbose: bool = False) -> Path:
     return EXT
 
 
+def build_tools(verbose: bool = False):
+    """Stand-alone measurement programs under tools/ (they link libbloomrast.so through the C-ABI only)."""
+    out = []
+    for name in ("sort_vs_cub", "probe_ffma2"):
+        src = ROOT / "tools" / f"{name}.cu"
+        exe = BUILD / name
+        if not src.exists() or (exe.exists() and exe.stat().st_mtime > max(src.stat().st_mtime, LIB.stat().st_mtime)):
+            continue
+        cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", str(src), f"-I{ROOT / 'include'}",
+               f"-L{PKG}", "-lbloomrast", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/..", "-o", str(exe)]
+        if verbose:
+            print(f"[build] nvcc tools/{name}.cu", flush=True)
+        subprocess.run(cmd, check=True)
+        out.append(exe)
+    return out
+
+
 def build_all(verbose: bool = False):
     lib = build_lib(verbose)
     ext = build_ext(verbose)
+    build_tools(verbose)
     return lib, ext
 
 

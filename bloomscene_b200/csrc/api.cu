@@ -35,6 +35,13 @@ struct HostSlot { // per thread: pinned word for the R readback + its event
 	int device = -1;
 	uint32_t* pinned = nullptr;
 	cudaEvent_t event = nullptr;
+	~HostSlot() // host threads come and go (one per lane of a view batch): give the pinned word and the event back
+	{
+		if (pinned != nullptr)
+			cudaFreeHost(pinned);
+		if (event != nullptr)
+			cudaEventDestroy(event);
+	}
 };
 thread_local HostSlot t_slot;
 
@@ -49,7 +56,9 @@ cudaError_t ensure_slot()
 	if (t_slot.pinned != nullptr) {
 		cudaFreeHost(t_slot.pinned);
 		cudaEventDestroy(t_slot.event);
-		t_slot = HostSlot{};
+		t_slot.pinned = nullptr;
+		t_slot.event = nullptr;
+		t_slot.device = -1;
 	}
 	e = cudaHostAlloc(reinterpret_cast<void**>(&t_slot.pinned), 64, cudaHostAllocDefault);
 	if (e != cudaSuccess)
@@ -67,6 +76,15 @@ struct StageTimer {
 	struct Pending { int stage; cudaEvent_t a, b; };
 	std::vector<Pending> pending;
 	std::vector<cudaEvent_t> pool;
+	~StageTimer()
+	{
+		for (auto& p : pending) {
+			cudaEventDestroy(p.a);
+			cudaEventDestroy(p.b);
+		}
+		for (cudaEvent_t e : pool)
+			cudaEventDestroy(e);
+	}
 	cudaEvent_t get()
 	{
 		if (!pool.empty()) {
@@ -118,29 +136,41 @@ std::mutex g_companion_mutex;
 std::map<std::pair<int, cudaStream_t>, Companion> g_companions;
 int g_companion_enabled = 1;
 
-// Returns nullptr when the blend should simply run on `stream`.
-Companion* companion_for(cudaStream_t stream)
+// Returns false when the blend should simply run on `stream`; otherwise `out` is a copy of the entry
+// (handles only: the table may be rebuilt by another thread at any time).
+bool companion_for(cudaStream_t stream, Companion& out)
 {
 	if (!g_companion_enabled || t_timer.enabled || stream == nullptr)
-		return nullptr;
+		return false;
 	int least = 0, greatest = 0, prio = 0, dev = 0;
 	if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess || least == greatest)
-		return nullptr;
+		return false;
 	if (cudaStreamGetPriority(stream, &prio) != cudaSuccess || prio >= least) // numerically lower = higher priority
-		return nullptr;
+		return false;
 	if (cudaGetDevice(&dev) != cudaSuccess)
-		return nullptr;
+		return false;
 	std::lock_guard<std::mutex> lock(g_companion_mutex);
+	if (g_companions.size() >= 64 && g_companions.find(std::make_pair(dev, stream)) == g_companions.end()) {
+		// callers that keep creating streams would grow the table without bound: drop it and start over
+		// (destroying a stream / event with work in flight is legal, the driver releases it afterwards)
+		for (auto& kv : g_companions) {
+			cudaStreamDestroy(kv.second.stream);
+			cudaEventDestroy(kv.second.before);
+			cudaEventDestroy(kv.second.after);
+		}
+		g_companions.clear();
+	}
 	Companion& c = g_companions[std::make_pair(dev, stream)];
 	if (c.stream == nullptr) {
 		if (cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, least) != cudaSuccess ||
 		    cudaEventCreateWithFlags(&c.before, cudaEventDisableTiming) != cudaSuccess ||
 		    cudaEventCreateWithFlags(&c.after, cudaEventDisableTiming) != cudaSuccess) {
 			c = Companion{};
-			return nullptr;
+			return false;
 		}
 	}
-	return &c;
+	out = c;
+	return true;
 }
 
 inline int fail_cuda(cudaError_t e)
@@ -601,12 +631,13 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	ba.n_contrib = n_contrib;
 	ba.out_color = out_color;
 	ba.out_depth = out_depth;
-	if (Companion* c = debug ? nullptr : companion_for(stream)) {
-		BRS_CUDA(cudaEventRecord(c->before, stream));
-		BRS_CUDA(cudaStreamWaitEvent(c->stream, c->before, 0));
-		BRS_CUDA(launch_blend_forward(ba, c->stream));
-		BRS_CUDA(cudaEventRecord(c->after, c->stream));
-		BRS_CUDA(cudaStreamWaitEvent(stream, c->after, 0));
+	Companion comp;
+	if (!debug && companion_for(stream, comp)) {
+		BRS_CUDA(cudaEventRecord(comp.before, stream));
+		BRS_CUDA(cudaStreamWaitEvent(comp.stream, comp.before, 0));
+		BRS_CUDA(launch_blend_forward(ba, comp.stream));
+		BRS_CUDA(cudaEventRecord(comp.after, comp.stream));
+		BRS_CUDA(cudaStreamWaitEvent(stream, comp.after, 0));
 	} else {
 		BRS_STAGE(BRS_STAGE_BLEND_FWD, launch_blend_forward(ba, stream), debug, stream);
 	}
@@ -634,11 +665,13 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 	const int M = g->shs ? view->sh_coeffs : 0;
 	const bool acc = grads->accumulate != 0;
 	const bool has_sr = g->scales != nullptr;
-	// plain mode needs every tensor; accumulate mode only those of the inputs that were given
-	if (radii == nullptr || grads->dL_dmeans2D == nullptr || grads->dL_dopacity == nullptr ||
-	    grads->dL_dmeans3D == nullptr || (M > 0 && grads->dL_dsh == nullptr) ||
-	    ((!acc || M == 0) && grads->dL_dcolors == nullptr) || ((!acc || !has_sr) && grads->dL_dcov3D == nullptr) ||
-	    ((!acc || has_sr) && (grads->dL_dscales == nullptr || grads->dL_drotations == nullptr)))
+	// plain mode needs every tensor; in accumulate mode every parameter sink is optional (a NULL sink
+	// = a frozen parameter whose gradient the caller does not want) and only dL_dmeans2D is required
+	if (radii == nullptr || grads->dL_dmeans2D == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	if (!acc && (grads->dL_dopacity == nullptr || grads->dL_dmeans3D == nullptr || (M > 0 && grads->dL_dsh == nullptr) ||
+	             grads->dL_dcolors == nullptr || grads->dL_dcov3D == nullptr || grads->dL_dscales == nullptr ||
+	             grads->dL_drotations == nullptr))
 		return BRS_ERR_INVALID_ARG;
 	const GeomLayout gl = geom_layout(P);
 	const ImageLayout il = image_layout(W, H);
@@ -678,12 +711,13 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 		bb.dL_ddepth = depth_grad ? dL_dout_depth : nullptr;
 		bb.out_depth = depth_grad ? grads->out_depth : nullptr;
 		bb.accum = accum;
-		if (Companion* c = debug ? nullptr : companion_for(stream)) {
-			BRS_CUDA(cudaEventRecord(c->before, stream));
-			BRS_CUDA(cudaStreamWaitEvent(c->stream, c->before, 0));
-			BRS_CUDA(launch_blend_backward(bb, c->stream));
-			BRS_CUDA(cudaEventRecord(c->after, c->stream));
-			BRS_CUDA(cudaStreamWaitEvent(stream, c->after, 0));
+		Companion comp;
+		if (!debug && companion_for(stream, comp)) {
+			BRS_CUDA(cudaEventRecord(comp.before, stream));
+			BRS_CUDA(cudaStreamWaitEvent(comp.stream, comp.before, 0));
+			BRS_CUDA(launch_blend_backward(bb, comp.stream));
+			BRS_CUDA(cudaEventRecord(comp.after, comp.stream));
+			BRS_CUDA(cudaStreamWaitEvent(stream, comp.after, 0));
 		} else {
 			BRS_STAGE(BRS_STAGE_BLEND_BWD, launch_blend_backward(bb, stream), debug, stream);
 		}

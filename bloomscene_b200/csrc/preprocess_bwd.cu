@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 			s_cam[t] = __ldg(a.viewmatrix + t);
 		else if (t < 32)
 			s_cam[t] = __ldg(a.projmatrix + t - 16);
-		else if (t < 35)
+		else if (t < 35 && a.campos != nullptr) // only the SH chain reads it; colors_precomp callers may pass none
 			s_cam[t] = __ldg(a.campos + t - 32);
 	}
 
@@ -434,32 +434,40 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 		} else if (visible) {
 			// float atomics (RED, no return value): several views may be adding into the same bucket from
 			// different streams at the same time
-			float* p3 = a.dL_dmeans3D + 3 * (size_t)idx;
-			atomicAdd(p3 + 0, o_mean3D.x);
-			atomicAdd(p3 + 1, o_mean3D.y);
-			atomicAdd(p3 + 2, o_mean3D.z);
-			atomicAdd(a.dL_dopacity + idx, o_opacity);
+			// a NULL sink is a parameter the caller froze: its gradient is dropped
+			if (a.dL_dmeans3D != nullptr) {
+				float* p3 = a.dL_dmeans3D + 3 * (size_t)idx;
+				atomicAdd(p3 + 0, o_mean3D.x);
+				atomicAdd(p3 + 1, o_mean3D.y);
+				atomicAdd(p3 + 2, o_mean3D.z);
+			}
+			if (a.dL_dopacity != nullptr)
+				atomicAdd(a.dL_dopacity + idx, o_opacity);
 			if (a.scales != nullptr) {
-				float* ps = a.dL_dscales + 3 * (size_t)idx;
-				atomicAdd(ps + 0, o_scale.x);
-				atomicAdd(ps + 1, o_scale.y);
-				atomicAdd(ps + 2, o_scale.z);
-				float* pr = a.dL_drotations + 4 * (size_t)idx;
-				if ((reinterpret_cast<uintptr_t>(a.dL_drotations) & 15u) == 0) {
-					red_add_v4(pr, o_rot.x, o_rot.y, o_rot.z, o_rot.w);
-				} else { // a bucket slice that is not 16-byte aligned (odd P)
-					atomicAdd(pr + 0, o_rot.x);
-					atomicAdd(pr + 1, o_rot.y);
-					atomicAdd(pr + 2, o_rot.z);
-					atomicAdd(pr + 3, o_rot.w);
+				if (a.dL_dscales != nullptr) {
+					float* ps = a.dL_dscales + 3 * (size_t)idx;
+					atomicAdd(ps + 0, o_scale.x);
+					atomicAdd(ps + 1, o_scale.y);
+					atomicAdd(ps + 2, o_scale.z);
 				}
-			} else {
+				if (a.dL_drotations != nullptr) {
+					float* pr = a.dL_drotations + 4 * (size_t)idx;
+					if ((reinterpret_cast<uintptr_t>(a.dL_drotations) & 15u) == 0) {
+						red_add_v4(pr, o_rot.x, o_rot.y, o_rot.z, o_rot.w);
+					} else { // a bucket slice that is not 16-byte aligned (odd P)
+						atomicAdd(pr + 0, o_rot.x);
+						atomicAdd(pr + 1, o_rot.y);
+						atomicAdd(pr + 2, o_rot.z);
+						atomicAdd(pr + 3, o_rot.w);
+					}
+				}
+			} else if (a.dL_dcov3D != nullptr) {
 				p = a.dL_dcov3D + 6 * (size_t)idx;
 #pragma unroll
 				for (int i = 0; i < 6; i++)
 					atomicAdd(p + i, o_cov[i]);
 			}
-			if (a.shs == nullptr) {
+			if (a.shs == nullptr && a.dL_dcolors != nullptr) {
 				p = a.dL_dcolors + 3 * (size_t)idx;
 				atomicAdd(p + 0, o_color.x);
 				atomicAdd(p + 1, o_color.y);

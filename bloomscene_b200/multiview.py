@@ -13,68 +13,13 @@ logic can be tested on CPU with an oracle-backed stand-in (tests only).
 """
 from __future__ import annotations
 
-from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, lane_streams
-from .synthetic import Camera, Scene, raster_settings
-
-_ORDER = ("means3D", "scales", "rotations", "opacities", "shs", "colors_precomp")
-
-
-class GaussianParams:
-    """Gaussian parameters packed in one flat fp32 buffer with a matching flat gradient bucket.
-
-    Each parameter tensor is a leaf view into `flat`, and its `.grad` is preset to the matching view
-    of `grad_bucket`, so every view's gradients land straight in the bucket (added by the kernel itself
-    with the native rasterizer, by autograd otherwise) and a single allreduce covers all parameters
-    ((44 + 12 M) bytes per Gaussian)."""
-
-    def __init__(self, scene: Scene):
-        tensors = {k: v for k, v in scene.tensors().items()}
-        self.names = [n for n in _ORDER if n in tensors]
-        self.sh_degree = scene.sh_degree
-        dev = scene.means3D.device
-        sizes = [tensors[n].numel() for n in self.names]
-        self.flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        self.grad_bucket = torch.zeros_like(self.flat)
-        self.tensors: Dict[str, torch.Tensor] = {}
-        self._zero_means2D = None
-        off = 0
-        for n, sz in zip(self.names, sizes):
-            seg = self.flat[off:off + sz].view(tensors[n].shape)
-            seg.copy_(tensors[n])
-            seg.requires_grad_(True)
-            seg.grad = self.grad_bucket[off:off + sz].view(tensors[n].shape)
-            self.tensors[n] = seg
-            off += sz
-
-    @property
-    def P(self) -> int:
-        return self.tensors["means3D"].shape[0]
-
-    def zero_grad(self):
-        self.grad_bucket.zero_()
-
-    def zero_means2D(self) -> torch.Tensor:
-        """The all-zero `means2D` input every view passes in (reference gaussian_renderer/__init__.py:224-229
-        creates a fresh zeros_like per call); it is only a gradient carrier, so one buffer serves all views."""
-        if self._zero_means2D is None:
-            self._zero_means2D = torch.zeros_like(self.tensors["means3D"].detach())
-        return self._zero_means2D
-
-    def grads(self) -> Dict[str, torch.Tensor]:
-        return {n: t.grad for n, t in self.tensors.items()}
-
-    def get(self, name: str) -> Optional[torch.Tensor]:
-        return self.tensors.get(name)
-
-
-def shard_views(n_views: int, rank: int, world: int) -> List[int]:
-    """Round-robin view assignment: rank r renders views r, r+N, r+2N, ..."""
-    return list(range(rank, n_views, world))
+from .rasterizer import GaussianRasterizationSettings, lane_pool, lane_streams
+from workload.params import GaussianParams, shard_views
+from workload.synthetic import Camera, raster_settings
 
 
 def default_loss(color: torch.Tensor, depth: torch.Tensor, Wc: torch.Tensor, Wd: torch.Tensor) -> torch.Tensor:
@@ -84,7 +29,7 @@ def default_loss(color: torch.Tensor, depth: torch.Tensor, Wc: torch.Tensor, Wd:
 def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: torch.Tensor, rasterizer_cls,
                       loss_fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor],
                       rank: int = 0, world: int = 1, group=None, allreduce: bool = True,
-                      streams: int = 4, host_threads: bool = False) -> Dict[str, object]:
+                      streams: int = 4, host_threads: bool = False, keep_means2D_grad: bool = False) -> Dict[str, object]:
     """Render this rank's slice of `cameras`, backpropagate `loss_fn(color, depth, view_index)`, sum the
     parameter gradients over ranks.  Returns the step loss (summed over all views), per-view radii
     counts and the number of views rendered locally.
@@ -117,7 +62,9 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
         loss = loss_fn(color, depth, vi)
         loss.backward()
         losses[lane] += loss.detach()
-        visible.append((vi, radii))
+        # per-view statistics for the caller's densification (reference scene/gaussian_model.py:742-759 reads
+        # viewspace_points.grad[:, :2] and radii > 0 after every view)
+        visible.append((vi, radii, means2D.grad if keep_means2D_grad else None))
 
     if n_lanes == 1:
         for vi in mine:
@@ -135,15 +82,19 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
                     for vi in mine[lane::n_lanes]:
                         one_view(vi, lane)
 
-            with ThreadPoolExecutor(max_workers=n_lanes) as pool:
-                for f in [pool.submit(drive, lane) for lane in range(n_lanes)]:
-                    f.result()
+            pool = lane_pool(dev, n_lanes)
+            for f in [pool.submit(drive, lane) for lane in range(n_lanes)]:
+                f.result()
         else:
             for j, vi in enumerate(mine):
                 with torch.cuda.stream(lanes[j % n_lanes]):
                     one_view(vi, j % n_lanes)
         for st in lanes:
             cur.wait_stream(st)
+        for _, radii, m2 in visible:  # allocated on a lane stream, handed to the caller's stream
+            radii.record_stream(cur)
+            if m2 is not None:
+                m2.record_stream(cur)
     loss_sum = losses[0]
     for extra in losses[1:]:
         loss_sum = loss_sum + extra
@@ -152,7 +103,8 @@ def view_sharded_step(params: GaussianParams, cameras: Sequence[Camera], bg: tor
 
         dist.all_reduce(params.grad_bucket, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)
-    return {"loss": loss_sum, "views": mine, "radii": visible}
+    return {"loss": loss_sum, "views": mine, "radii": [(vi, r) for vi, r, _ in visible],
+            "means2D_grad": [(vi, m2) for vi, _, m2 in visible] if keep_means2D_grad else None}
 
 
 def _slice_bounds(numel: int, rank: int, world: int):

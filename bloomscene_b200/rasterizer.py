@@ -60,6 +60,17 @@ def _guarded(native_fn, args, debug: bool, dump_file: str, message: str):
 
 
 _LANE_STREAMS = {}
+_LANE_POOLS = {}
+
+
+def lane_pool(dev: torch.device, n: int) -> ThreadPoolExecutor:
+    """One long-lived pool of `n` host threads per device for driving the lane streams (a fresh executor
+    per call would pay thread start-up, and the library's per-thread pinned slot, on every step)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), n)
+    pool = _LANE_POOLS.get(key)
+    if pool is None:
+        pool = _LANE_POOLS[key] = ThreadPoolExecutor(max_workers=n, thread_name_prefix="brs-lane")
+    return pool
 
 
 def lane_streams(dev: torch.device, n: int):
@@ -112,19 +123,25 @@ def bind(_C) -> SimpleNamespace:
                 # extension: parameter gradients are added in place to the caller's sinks by the kernel
                 # (brs_grads.accumulate); autograd only carries the per-view means2D gradient
                 k = ctx.grad_sink
-                d_means2D = _C.rasterize_gaussians_backward_accumulate(
-                    rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
-                    rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, sh, rs.sh_degree,
-                    rs.campos, geom, ctx.num_rendered, binning, image, rs.debug,
-                    k.get("means3D"), k.get("colors_precomp"), k.get("opacities"), k.get("cov3D_precomp"), k.get("shs"),
-                    k.get("scales"), k.get("rotations"), out_depth)
+                d_means2D = _guarded(
+                    _C.rasterize_gaussians_backward_accumulate,
+                    (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                     rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, sh, rs.sh_degree,
+                     rs.campos, geom, ctx.num_rendered, binning, image, rs.debug,
+                     k.get("means3D"), k.get("colors_precomp"), k.get("opacities"), k.get("cov3D_precomp"), k.get("shs"),
+                     k.get("scales"), k.get("rotations"), out_depth),
+                    rs.debug, "snapshot_bw.dump",
+                    "\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 return None, d_means2D, None, None, None, None, None, None, None, None, None
             if ctx.depth_gradient:
                 # extension: grad_depth is back-propagated through the depth image (default off = reference)
-                g = _C.rasterize_gaussians_backward_depth(
-                    rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
-                    rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, sh, rs.sh_degree,
-                    rs.campos, geom, ctx.num_rendered, binning, image, rs.debug, out_depth)
+                g = _guarded(
+                    _C.rasterize_gaussians_backward_depth,
+                    (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                     rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth, sh, rs.sh_degree,
+                     rs.campos, geom, ctx.num_rendered, binning, image, rs.debug, out_depth),
+                    rs.debug, "snapshot_bw.dump",
+                    "\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 d_means2D, d_colors, d_opacities, d_means3D, d_cov3D, d_sh, d_scales, d_rotations = g
                 return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None, None
             g = _guarded(
@@ -261,9 +278,9 @@ def bind(_C) -> SimpleNamespace:
                             one(j, views[j])
 
                 if host_threads:
-                    with ThreadPoolExecutor(max_workers=n_lanes) as pool:
-                        for f in [pool.submit(drive, lane) for lane in range(n_lanes)]:
-                            f.result()
+                    pool = lane_pool(dev, n_lanes)
+                    for f in [pool.submit(drive, lane) for lane in range(n_lanes)]:
+                        f.result()
                 else:
                     for j, rs in enumerate(views):
                         with torch.cuda.stream(lanes[j % n_lanes]):

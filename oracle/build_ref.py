@@ -71,6 +71,32 @@ def so_path() -> Path:
     return OUT / f"{MODULE}.so"
 
 
+PKG = "ref_depth_diff_gaussian_rasterization"
+
+
+def write_reference_package() -> Path | None:
+    """Place the reference's OWN Python wrapper (depth_diff_gaussian_rasterization/__init__.py, every
+    line as it is in /root/reference) into the git-ignored oracle/_ref/pkg/, with its one import line
+    `from . import _C` redirected to oracle/_ref/_ref_C.so.  bench.py --impl reference imports this
+    package and nothing of the product, so the reference arm runs the reference's stock code path."""
+    src = REF_RAST / "depth_diff_gaussian_rasterization" / "__init__.py"
+    dst = OUT / "pkg" / PKG / "__init__.py"
+    if not src.exists():
+        return dst if dst.exists() else None
+    text = src.read_text()
+    needle = "from . import _C\n"
+    assert text.count(needle) == 1, "reference wrapper changed: expected exactly one `from . import _C`"
+    loader = (
+        "import importlib.util as _ilu, os as _os\n"
+        f"_spec = _ilu.spec_from_file_location('{MODULE}', _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), '..', '..', '{MODULE}.so'))\n"
+        "_C = _ilu.module_from_spec(_spec)\n"
+        "_spec.loader.exec_module(_C)\n"
+    )
+    dst.parent.mkdir(parents=True, exist_ok=True)
+    dst.write_text(text.replace(needle, loader))
+    return dst
+
+
 def build(verbose: bool = True) -> Path | None:
     """Build oracle/_ref/_ref_C.so if /root/reference is present; return its path (or None)."""
     if not REF_RAST.exists():
@@ -79,6 +105,7 @@ def build(verbose: bool = True) -> Path | None:
     OUT.mkdir(parents=True, exist_ok=True)
     stamp = OUT / "stamp.txt"
     fp = _fingerprint()
+    write_reference_package()
     if so_path().exists() and stamp.exists() and stamp.read_text().strip() == fp:
         return so_path()
 
@@ -131,6 +158,23 @@ def build(verbose: bool = True) -> Path | None:
     if verbose:
         print("[oracle/_ref] built", so_path(), flush=True)
     return so_path()
+
+
+def load_reference_package():
+    """Import the reference's own Python package from oracle/_ref/pkg (see write_reference_package);
+    None if it was never built."""
+    init = OUT / "pkg" / PKG / "__init__.py"
+    if not init.exists() or not so_path().exists():
+        return None
+    import importlib.util
+
+    import torch  # noqa: F401
+
+    spec = importlib.util.spec_from_file_location(PKG, str(init), submodule_search_locations=[str(init.parent)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[PKG] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def load():

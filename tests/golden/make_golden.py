@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import parity_lib as pl  # noqa: E402
-from bloomscene_b200 import synthetic  # noqa: E402
+from workload import synthetic  # noqa: E402
 from oracle import ref_state  # noqa: E402
 
 

@@ -12,7 +12,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import parity_lib as pl  # noqa: E402
-from bloomscene_b200 import synthetic  # noqa: E402
+from workload import synthetic  # noqa: E402
 
 
 def main():

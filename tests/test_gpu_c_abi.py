@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import parity_lib as pl
-from bloomscene_b200 import synthetic
+from workload import synthetic
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

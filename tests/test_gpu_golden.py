@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import parity_lib as pl
-from bloomscene_b200 import synthetic
+from workload import synthetic
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 import parity_lib as pl
-from bloomscene_b200 import synthetic
+from workload import synthetic
 
 pytestmark = pytest.mark.gpu
 
@@ -23,9 +23,14 @@ DEV = "cuda:0"
 
 
 def _ref_or_skip():
+    """The reference's own CUDA build.  On a GPU box its absence is a FAILURE (a green run with the parity
+    tests skipped would prove nothing); BRS_ALLOW_NO_REF=1 turns that into a skip for ad-hoc runs."""
     ref = pl.reference()
     if ref is None:
-        pytest.skip("oracle/_ref/_ref_C.so not built (needs /root/reference at build time)")
+        msg = "oracle/_ref/_ref_C.so not built (needs /root/reference at build time: python -m oracle.build_ref)"
+        if os.environ.get("BRS_ALLOW_NO_REF") == "1":
+            pytest.skip(msg)
+        pytest.fail(msg)
     return ref
 
 
@@ -36,8 +41,6 @@ def _assert_stage_parity(rep):
         if k in rep:
             assert rep[k] == 0, (k, rep)
     assert rep["R_ours"] == rep["R_ref"], rep
-    if "unsorted_keys_multiset_equal" in rep:
-        assert rep["unsorted_keys_multiset_equal"]
     assert rep.get("color_maxabs", 0.0) <= pl.COLOR_TOL, rep
     assert rep.get("depth_maxabs", 0.0) <= pl.COLOR_TOL, rep
 
@@ -107,6 +110,37 @@ def test_full_size_1m_1080p_sh3_vs_reference_cuda():
     Wc, Wd = (t.to(DEV) for t in synthetic.loss_weights(cam.image_width, cam.image_height))
     _assert_stage_parity(pl.compare_stages(scene, cam, bg))
     _assert_grad_parity(pl.compare_autograd(scene, cam, bg, Wc, Wd))
+
+
+def test_config_D_3m_4k_sh3_vs_reference_cuda():
+    """BASELINE.json configs[3]: 3M Gaussians, SH3, 3840x2160 (32 400 tiles, 47 key bits in the reference's
+    sort: getHigherMsb, rasterizer_impl.cu:35-50), band scene seen from two yaws of the rotate360 trajectory."""
+    _ref_or_skip()
+    scene = synthetic.config_scene("D").to(DEV)
+    cams = synthetic.config_cameras("D")
+    bg = torch.zeros(3, device=DEV)
+    for k in (0, 37):
+        cam = cams[k].to(DEV)
+        rep = pl.compare_stages(scene, cam, bg)
+        assert rep["visible"] > 100_000 and rep["R_ref"] > 1_000_000, rep
+        _assert_stage_parity(rep)
+        torch.cuda.empty_cache()
+
+
+def test_config_B_500k_precomp_512_vs_reference_cuda():
+    """BASELINE.json configs[1]: BloomScene's own working point — 500K neural Gaussians with colors_precomp,
+    512x512, rotate360 yaws; ~88 % of the Gaussians are outside any one view (culled)."""
+    _ref_or_skip()
+    scene = synthetic.config_scene("B").to(DEV)
+    cams = synthetic.config_cameras("B")
+    bg = torch.zeros(3, device=DEV)
+    Wc, Wd = (t.to(DEV) for t in synthetic.loss_weights(512, 512))
+    for k in (0, 29, 60, 101):
+        cam = cams[k].to(DEV)
+        rep = pl.compare_stages(scene, cam, bg)
+        assert 0 < rep["visible"] < scene.P // 4, rep
+        _assert_stage_parity(rep)
+        _assert_grad_parity(pl.compare_autograd(scene, cam, bg, Wc, Wd))
 
 
 def test_edge_cases_vs_reference_cuda():

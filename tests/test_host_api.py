@@ -118,7 +118,7 @@ def test_python_argument_errors_match_reference_messages():
 
 def test_autograd_plumbing_with_oracle_backend():
     """The shared Python wrapper routes gradients to the right inputs (reference __init__.py:144-154)."""
-    from bloomscene_b200 import synthetic
+    from workload import synthetic
     from bloomscene_b200.rasterizer import GaussianRasterizationSettings, bind
     from oracle_backend import OracleBackend
 
@@ -161,7 +161,7 @@ def test_autograd_plumbing_with_oracle_backend():
 
 def test_render_views_equals_single_view_calls_with_oracle_backend():
     """render_views (forward-only batch entry point) returns exactly what one GaussianRasterizer call per view returns."""
-    from bloomscene_b200 import synthetic
+    from workload import synthetic
     from bloomscene_b200.rasterizer import GaussianRasterizationSettings, bind
     from oracle_backend import OracleBackend
 
@@ -189,7 +189,7 @@ def test_render_views_equals_single_view_calls_with_oracle_backend():
 def test_opt_in_depth_gradient_with_oracle_backend():
     """depth_gradient=True (extension, default off): a depth-only loss reaches the parameters, and the
     oracle's derivative agrees with central finite differences of its own forward."""
-    from bloomscene_b200 import synthetic
+    from workload import synthetic
     from bloomscene_b200.rasterizer import GaussianRasterizationSettings, bind
     from oracle_backend import OracleBackend
 

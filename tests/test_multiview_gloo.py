@@ -21,7 +21,7 @@ def _free_port():
 
 
 def _setup():
-    from bloomscene_b200 import synthetic
+    from workload import synthetic
     from bloomscene_b200.multiview import GaussianParams
     from bloomscene_b200.rasterizer import bind
     from oracle_backend import OracleBackend

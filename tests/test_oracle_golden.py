@@ -87,7 +87,7 @@ def test_empty_scene():
 def test_mark_visible_and_filter_agree_with_forward():
     import torch
 
-    from bloomscene_b200 import synthetic
+    from workload import synthetic
 
     scene = synthetic.make_scene(3000, "band", "precomp", -3.0, seed=9)
     cam = synthetic.yaw_camera(96, 64, 0.4)

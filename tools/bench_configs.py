@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 import parity_lib as pl  # noqa: E402
-from bloomscene_b200 import synthetic  # noqa: E402
+from workload import synthetic  # noqa: E402
 
 
 def render_loop(api, scene, cams, bg, reps=1):

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import parity_lib as pl
-from bloomscene_b200 import synthetic
+from workload import synthetic
 from bloomscene_b200.multiview import GaussianParams, view_sharded_step
 
 dev = torch.device("cuda:0")

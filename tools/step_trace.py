@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--views", type=int, default=8)
     a = ap.parse_args()
     import bloomscene_b200
-    from bloomscene_b200 import synthetic
+    from workload import synthetic
     from bloomscene_b200.multiview import GaussianParams, view_sharded_step
 
     api = bloomscene_b200._api

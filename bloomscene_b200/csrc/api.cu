@@ -29,6 +29,7 @@ namespace brs {
 namespace {
 
 thread_local long long t_launches = 0;
+thread_local long long t_fwd_stats[4] = {0, 0, 0, 0}; // exact, optimistic, overflow re-runs, deferred
 thread_local int t_last_cuda_error = 0;
 
 struct HostSlot { // per thread: pinned word for the R readback + its event
@@ -239,16 +240,6 @@ ImageLayout image_layout(int W, int H)
 
 size_t binning_bytes(size_t R) { return align_up(sizeof(uint32_t) * (R ? R : 1), 256); }
 
-// reference getHigherMsb (rasterizer_impl.cu:35-50) yields the bit count the tile id is sorted on;
-// any bit count >= ceil(log2(#tiles)) gives the same order, so use the exact one.
-int tile_bits(uint32_t num_tiles)
-{
-	int b = 0;
-	while ((1ull << b) < (unsigned long long)num_tiles)
-		b++;
-	return b < 1 ? 1 : b;
-}
-
 int validate_view(const brs_view* v, bool need_campos_bg)
 {
 	if (v == nullptr || v->viewmatrix == nullptr || v->projmatrix == nullptr)
@@ -330,18 +321,17 @@ size_t brs_binning_bytes(int R) { return binning_bytes(R < 0 ? 0 : (size_t)R); }
 size_t brs_image_bytes(int W, int H) { return image_layout(W, H).total; }
 size_t brs_sort_scratch_bytes(int n) { return sort_scratch_bytes(n < 0 ? 0 : (size_t)n); }
 
-// sorted keys (final) + first-pass keys/values + the sort's own scratch (tables + ping-pong pair)
-static size_t depth_scratch_bytes(size_t P) { return 3 * align_up(sizeof(uint32_t) * P, 256) + sort_scratch_bytes(P); }
-// R1 = supertile instances (what the coarse level sorts); never more than the tile instances R.
-static size_t instance_scratch_bytes(size_t P, size_t R1, uint32_t grid_x, uint32_t grid_y)
+// Scratch of one forward with the given capacities: [zeroed: depth sort | instance levels][plain: both].
+static size_t forward_scratch_bytes(size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y, int depth_passes)
 {
-	return 4 * align_up(sizeof(uint32_t) * R1, 256) + sort_scratch_bytes(R1) + emit_scratch_bytes(P) +
-	       fine_scratch_bytes(R1, grid_x, grid_y);
+	return depth_zero_bytes(P, depth_passes) + inst_zero_bytes(P, R1_cap, grid_x, grid_y) + depth_plain_bytes(P) +
+	       inst_plain_bytes(P, R1_cap, grid_x, grid_y);
 }
 size_t brs_forward_scratch_bytes(int P, int R, int W, int H)
 {
 	const uint32_t gx = W > 0 ? (W + TILE_X - 1) / TILE_X : 0, gy = H > 0 ? (H + TILE_Y - 1) / TILE_Y : 0;
-	return depth_scratch_bytes(P < 0 ? 0 : P) + instance_scratch_bytes(P < 0 ? 0 : P, R < 0 ? 0 : R, gx, gy);
+	// R1 (supertile instances) never exceeds R (tile instances)
+	return forward_scratch_bytes(P < 0 ? 0 : P, R < 0 ? 0 : R, gx, gy, 4);
 }
 size_t brs_backward_scratch_bytes(int P) { return align_up(sizeof(float) * ACCUM_STRIDE * (P < 0 ? 0 : (size_t)P), 256); }
 
@@ -434,8 +424,176 @@ int brs_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_
 	return BRS_OK;
 }
 
+} // extern "C"
+
+namespace {
+
+// High-water marks of the instance counts per (device, P, W, H): what sizes an optimistic forward.
+struct Marks {
+	uint32_t R = 0, R1 = 0, key_bits = 0;
+};
+struct MarksKey {
+	int dev, P, W, H;
+	bool operator<(const MarksKey& o) const
+	{
+		return dev != o.dev ? dev < o.dev : (P != o.P ? P < o.P : (W != o.W ? W < o.W : H < o.H));
+	}
+};
+std::mutex g_marks_mutex;
+std::map<MarksKey, Marks> g_marks;
+
+bool lookup_marks(const MarksKey& k, Marks& out)
+{
+	std::lock_guard<std::mutex> lock(g_marks_mutex);
+	auto it = g_marks.find(k);
+	if (it == g_marks.end())
+		return false;
+	out = it->second;
+	return true;
+}
+void raise_marks(const MarksKey& k, uint32_t R, uint32_t R1, uint32_t key_bits)
+{
+	std::lock_guard<std::mutex> lock(g_marks_mutex);
+	if (g_marks.size() >= 256 && g_marks.find(k) == g_marks.end())
+		g_marks.clear();
+	Marks& m = g_marks[k];
+	m.R = R > m.R ? R : m.R;
+	m.R1 = R1 > m.R1 ? R1 : m.R1;
+	m.key_bits = key_bits > m.key_bits ? key_bits : m.key_bits;
+}
+
+struct Caps {
+	uint32_t R_cap, R1_cap;
+	int depth_passes;
+};
+int passes_for_bits(uint32_t key_bits)
+{
+	int p = ((int)key_bits + 7) / 8;
+	return p < 2 ? 2 : (p > 4 ? 4 : p); // >= 2: see launch_depth_sort_begin
+}
+Caps caps_from_marks(const Marks& m)
+{
+	Caps c;
+	c.R_cap = m.R + m.R / 4 + 4096;
+	c.R1_cap = m.R1 + m.R1 / 4 + 4096;
+	c.depth_passes = passes_for_bits(m.key_bits + 1);
+	return c;
+}
+
+struct ForwardCtx {
+	const brs_view* view;
+	int P, W, H;
+	uint32_t grid_x, grid_y;
+	bool debug;
+	brs_alloc_fn alloc;
+	void* alloc_ctx;
+	brs_fwd_state* state;
+	cudaStream_t stream;
+	char* geom;
+	char* image;
+	GeomLayout gl;
+	ImageLayout il;
+	float* out_color;
+	float* out_depth;
+};
+
+// Everything after preprocess, sized by `caps`: depth sort -> emission -> coarse sort -> fine binning ->
+// blend.  No host wait in here.  If `report` is given, the header (counts + overflow word) is copied to
+// it right after the depth sort's histogram kernel has judged the capacities.
+int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* report, cudaEvent_t report_event)
+{
+	cudaStream_t stream = c.stream;
+	const bool debug = c.debug;
+	uint32_t* hdr = reinterpret_cast<uint32_t*>(c.geom + c.gl.header);
+	char* binning = static_cast<char*>(c.alloc(c.alloc_ctx, BRS_BUF_BINNING, binning_bytes(caps.R_cap)));
+	if (binning == nullptr)
+		return BRS_ERR_ALLOC;
+	c.state->binning = binning;
+	c.state->binning_bytes = binning_bytes(caps.R_cap);
+
+	BinPlan pl{};
+	pl.P = (uint32_t)c.P;
+	pl.R1_cap = caps.R1_cap;
+	pl.R_cap = caps.R_cap;
+	pl.grid_x = c.grid_x;
+	pl.grid_y = c.grid_y;
+	pl.ns_x = supertiles(c.grid_x);
+	pl.ns = pl.ns_x * supertiles(c.grid_y);
+	pl.depth_passes = caps.depth_passes;
+	pl.hdr = hdr;
+	pl.depth_key = reinterpret_cast<const uint32_t*>(c.geom + c.gl.depth_key);
+	pl.rect = reinterpret_cast<const uint2*>(c.geom + c.gl.rect);
+	pl.order = reinterpret_cast<uint32_t*>(c.geom + c.gl.order);
+	pl.point_list = reinterpret_cast<uint32_t*>(binning);
+	pl.ranges = reinterpret_cast<uint2*>(c.image + c.il.ranges);
+
+	const bool have_grid = c.grid_x * c.grid_y > 0;
+	if (have_grid) {
+		const size_t dz = depth_zero_bytes(c.P, caps.depth_passes), iz = inst_zero_bytes(c.P, caps.R1_cap, c.grid_x, c.grid_y);
+		const size_t dp = depth_plain_bytes(c.P);
+		char* scratch = static_cast<char*>(
+		    c.alloc(c.alloc_ctx, BRS_BUF_SCRATCH, forward_scratch_bytes(c.P, caps.R1_cap, c.grid_x, c.grid_y, caps.depth_passes)));
+		if (scratch == nullptr)
+			return BRS_ERR_ALLOC;
+		BRS_CUDA(cudaMemsetAsync(scratch, 0, dz + iz, stream)); // tickets, histograms, look-back status words
+		pl.d = carve_depth_scratch(scratch, scratch + dz + iz, c.P, caps.depth_passes);
+		pl.i = carve_inst_scratch(scratch + dz, scratch + dz + iz + dp, c.P, caps.R1_cap, c.grid_x, c.grid_y);
+
+		BRS_STAGE(BRS_STAGE_DEPTH_SORT, launch_depth_sort_begin(pl, caps.depth_passes, stream), debug, stream);
+		if (report != nullptr) {
+			BRS_CUDA(cudaMemcpyAsync(report, hdr, HDR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+			if (report_event != nullptr)
+				BRS_CUDA(cudaEventRecord(report_event, stream));
+		}
+		BRS_STAGE(BRS_STAGE_DEPTH_SORT, launch_depth_sort_rest(pl, stream), debug, stream);
+		BRS_STAGE(BRS_STAGE_COARSE_EMIT, launch_emit(pl, stream), debug, stream);
+		BRS_STAGE(BRS_STAGE_COARSE_SORT, launch_coarse_sort(pl, stream), debug, stream);
+		// also writes the (0,0) ranges of empty tiles (reference: cudaMemset, rasterizer_impl.cu:311)
+		BRS_STAGE(BRS_STAGE_FINE_BIN, launch_fine_binning(pl, stream), debug, stream);
+	} else if (report != nullptr) {
+		BRS_CUDA(cudaMemcpyAsync(report, hdr, HDR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		if (report_event != nullptr)
+			BRS_CUDA(cudaEventRecord(report_event, stream));
+	}
+
+	BlendFwdArgs ba{};
+	ba.ranges = pl.ranges;
+	ba.point_list = pl.point_list;
+	ba.records = reinterpret_cast<const float4*>(c.geom + c.gl.records);
+	ba.bg = c.view->bg;
+	ba.W = c.W;
+	ba.H = c.H;
+	ba.grid_x = c.grid_x;
+	ba.grid_y = c.grid_y;
+	ba.final_T = reinterpret_cast<float*>(c.image + c.il.final_T);
+	ba.n_contrib = reinterpret_cast<uint32_t*>(c.image + c.il.n_contrib);
+	ba.out_color = c.out_color;
+	ba.out_depth = c.out_depth;
+	Companion comp;
+	if (!debug && companion_for(stream, comp)) {
+		BRS_CUDA(cudaEventRecord(comp.before, stream));
+		BRS_CUDA(cudaStreamWaitEvent(comp.stream, comp.before, 0));
+		BRS_CUDA(launch_blend_forward(ba, comp.stream));
+		BRS_CUDA(cudaEventRecord(comp.after, comp.stream));
+		BRS_CUDA(cudaStreamWaitEvent(stream, comp.after, 0));
+	} else {
+		BRS_STAGE(BRS_STAGE_BLEND_FWD, launch_blend_forward(ba, stream), debug, stream);
+	}
+	return BRS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
 int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, float* out_depth, int* radii,
                 brs_alloc_fn alloc, void* alloc_ctx, brs_fwd_state* state, brs_stream stream)
+{
+	return brs_forward_ex(view, g, out_color, out_depth, radii, alloc, alloc_ctx, state, nullptr, stream);
+}
+
+int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_color, float* out_depth, int* radii,
+                   brs_alloc_fn alloc, void* alloc_ctx, brs_fwd_state* state, const brs_fwd_options* opt, brs_stream stream)
 {
 	int st = validate_view(view, true);
 	if (st != BRS_OK)
@@ -444,6 +602,11 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	if (st != BRS_OK)
 		return st;
 	if (alloc == nullptr || state == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	const int mode = opt ? opt->mode : BRS_FWD_AUTO;
+	if (mode != BRS_FWD_AUTO && mode != BRS_FWD_EXACT && mode != BRS_FWD_DEFERRED)
+		return BRS_ERR_INVALID_ARG;
+	if (mode == BRS_FWD_DEFERRED && opt->report == nullptr)
 		return BRS_ERR_INVALID_ARG;
 	const int W = view->image_width, H = view->image_height, P = g->P;
 	const size_t npix = (size_t)W * H;
@@ -460,33 +623,39 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 			BRS_CUDA(cudaMemsetAsync(out_color, 0, sizeof(float) * NUM_CHANNELS * npix, stream));
 			BRS_CUDA(cudaMemsetAsync(out_depth, 0, sizeof(float) * npix, stream));
 		}
+		if (mode == BRS_FWD_DEFERRED)
+			memset(opt->report, 0, HDR_WORDS * sizeof(uint32_t));
 		return BRS_OK;
 	}
 
-	const uint32_t grid_x = (W + TILE_X - 1) / TILE_X, grid_y = (H + TILE_Y - 1) / TILE_Y;
-	const GeomLayout gl = geom_layout(P);
-	const ImageLayout il = image_layout(W, H);
+	ForwardCtx c{};
+	c.view = view;
+	c.P = P;
+	c.W = W;
+	c.H = H;
+	c.grid_x = (W + TILE_X - 1) / TILE_X;
+	c.grid_y = (H + TILE_Y - 1) / TILE_Y;
+	c.debug = debug;
+	c.alloc = alloc;
+	c.alloc_ctx = alloc_ctx;
+	c.state = state;
+	c.stream = stream;
+	c.gl = geom_layout(P);
+	c.il = image_layout(W, H);
+	c.out_color = out_color;
+	c.out_depth = out_depth;
 
-	char* geom = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_GEOM, gl.total));
-	char* image = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_IMAGE, il.total));
-	if (geom == nullptr || image == nullptr)
+	c.geom = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_GEOM, c.gl.total));
+	c.image = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_IMAGE, c.il.total));
+	if (c.geom == nullptr || c.image == nullptr)
 		return BRS_ERR_ALLOC;
-	state->geom = geom;
-	state->geom_bytes = gl.total;
-	state->image = image;
-	state->image_bytes = il.total;
+	state->geom = c.geom;
+	state->geom_bytes = c.gl.total;
+	state->image = c.image;
+	state->image_bytes = c.il.total;
 
-	uint32_t* d_total = reinterpret_cast<uint32_t*>(geom + gl.header);
-	float4* records = reinterpret_cast<float4*>(geom + gl.records);
-	uint32_t* depth_key = reinterpret_cast<uint32_t*>(geom + gl.depth_key);
-	uint2* rect = reinterpret_cast<uint2*>(geom + gl.rect);
-	uint32_t* order = reinterpret_cast<uint32_t*>(geom + gl.order);
-	uint2* ranges = reinterpret_cast<uint2*>(image + il.ranges);
-	float* final_T = reinterpret_cast<float*>(image + il.final_T);
-	uint32_t* n_contrib = reinterpret_cast<uint32_t*>(image + il.n_contrib);
-
-	BRS_CUDA(ensure_slot());
-	BRS_CUDA(cudaMemsetAsync(geom + gl.header, 0, HEADER_BYTES, stream));
+	uint32_t* hdr = reinterpret_cast<uint32_t*>(c.geom + c.gl.header);
+	BRS_CUDA(cudaMemsetAsync(hdr, 0, HEADER_BYTES, stream));
 
 	PreprocessArgs pa{};
 	pa.P = P;
@@ -509,139 +678,108 @@ int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, 
 	pa.tan_fovy = view->tanfovy;
 	pa.focal_y = H / (2.0f * view->tanfovy); // rasterizer_impl.cu:223-224
 	pa.focal_x = W / (2.0f * view->tanfovx);
-	pa.grid_x = grid_x;
-	pa.grid_y = grid_y;
+	pa.grid_x = c.grid_x;
+	pa.grid_y = c.grid_y;
 	pa.prefiltered = view->prefiltered;
 	pa.radii = radii;
-	pa.records = records;
-	pa.depth_key = depth_key;
-	pa.rect = rect;
-	pa.total_tiles = d_total;
+	pa.records = reinterpret_cast<float4*>(c.geom + c.gl.records);
+	pa.depth_key = reinterpret_cast<uint32_t*>(c.geom + c.gl.depth_key);
+	pa.rect = reinterpret_cast<uint2*>(c.geom + c.gl.rect);
+	pa.total_tiles = hdr;
 	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
 
-	// R, R1 and the depth-key range leave for the host now.  The first radix pass of the depth sort (low
-	// 8 key bits) needs none of them and keeps the GPU busy during the host round trip.
-	BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, d_total, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	BRS_CUDA(cudaEventRecord(t_slot.event, stream));
+	// ---- deferred: the caller's capacities (or the high-water marks), no host wait at all ----
+	int dev = 0;
+	BRS_CUDA(cudaGetDevice(&dev));
+	const MarksKey key{dev, P, W, H};
+	Marks marks;
+	const bool have_marks = lookup_marks(key, marks);
+	if (mode == BRS_FWD_DEFERRED) {
+		Caps caps = caps_from_marks(marks); // zero marks -> the 4096-instance floor
+		if (opt->R_cap > 0)
+			caps.R_cap = (uint32_t)opt->R_cap;
+		if (opt->R1_cap > 0)
+			caps.R1_cap = (uint32_t)opt->R1_cap;
+		if (opt->depth_bits > 0)
+			caps.depth_passes = passes_for_bits((uint32_t)opt->depth_bits);
+		if (caps.R_cap > (1u << 30) || caps.R1_cap > (1u << 30))
+			return BRS_ERR_UNSUPPORTED;
+		state->num_rendered = -1; // on the device; the caller reads it from `report` once the stream has passed it
+		t_fwd_stats[3]++;
+		return enqueue_binning_and_blend(c, caps, opt->report, nullptr);
+	}
 
-	char* scratch1 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, depth_scratch_bytes(P)));
-	if (scratch1 == nullptr)
-		return BRS_ERR_ALLOC;
-	const size_t pb = align_up(sizeof(uint32_t) * (size_t)P, 256);
-	uint32_t* sorted_depth = reinterpret_cast<uint32_t*>(scratch1);
-	uint32_t* first_keys = reinterpret_cast<uint32_t*>(scratch1 + pb);
-	uint32_t* first_vals = reinterpret_cast<uint32_t*>(scratch1 + 2 * pb);
-	char* depth_sort_scratch = scratch1 + 3 * pb;
-	// culled Gaussians (key 0xFFFFFFFF) are dropped here: the later passes and the emission only see
-	// the V visible ones
-	BRS_STAGE(BRS_STAGE_DEPTH_SORT,
-	          sort_pass(depth_key, nullptr, first_keys, first_vals, (size_t)P, 0u, 0, 8, depth_sort_scratch, stream, true,
-	                    DEPTH_KEY_CULLED),
-	          debug, stream);
-
-	BRS_CUDA(cudaEventSynchronize(t_slot.event)); // the one host wait (reference: rasterizer_impl.cu:282)
-	const uint32_t R = t_slot.pinned[0], R1 = t_slot.pinned[1];
-	const uint32_t key_min = ~t_slot.pinned[2], key_max = t_slot.pinned[3];
-	const uint32_t V = t_slot.pinned[4]; // visible Gaussians = entries that survived the first pass
+	BRS_CUDA(ensure_slot());
+	Caps caps{};
+	bool counts_known = false;
+	if (mode == BRS_FWD_AUTO && have_marks) {
+		// ---- optimistic: everything is enqueued with capacities from the high-water marks; the host then
+		// waits for the header, which left the device right after preprocess + one histogram kernel, while
+		// the GPU still has the sort, the binning and the blend queued behind it ----
+		caps = caps_from_marks(marks);
+		t_fwd_stats[1]++;
+		st = enqueue_binning_and_blend(c, caps, t_slot.pinned, t_slot.event);
+		if (st != BRS_OK)
+			return st;
+		BRS_CUDA(cudaEventSynchronize(t_slot.event));
+		counts_known = true;
+		if (t_slot.pinned[HDR_OVERFLOW] == 0) {
+			state->num_rendered = (int)t_slot.pinned[HDR_R];
+			raise_marks(key, t_slot.pinned[HDR_R], t_slot.pinned[HDR_R1], t_slot.pinned[HDR_KEY_BITS]);
+			return BRS_OK;
+		}
+		// a capacity was too small: what was enqueued is memory-safe but wrong; run it again with the exact sizes
+		t_fwd_stats[2]++;
+	} else {
+		t_fwd_stats[0]++;
+		// ---- exact: wait for the counts right after preprocess (the reference's one host wait,
+		// rasterizer_impl.cu:282), then size everything exactly ----
+		BRS_CUDA(cudaMemcpyAsync(t_slot.pinned, hdr, HDR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		BRS_CUDA(cudaEventRecord(t_slot.event, stream));
+		BRS_CUDA(cudaEventSynchronize(t_slot.event));
+	}
+	const uint32_t R = t_slot.pinned[HDR_R], R1 = t_slot.pinned[HDR_R1], V = t_slot.pinned[HDR_V];
 	if (R > (1u << 30))
 		return BRS_ERR_UNSUPPORTED;
+	uint32_t key_bits = 8;
+	if (counts_known) {
+		key_bits = t_slot.pinned[HDR_KEY_BITS];
+	} else if (V > 0) {
+		const uint32_t key_min = ~t_slot.pinned[HDR_KEY_INVMIN], key_max = t_slot.pinned[HDR_KEY_MAX];
+		const uint32_t span = key_max - (key_min & ~0xFFu);
+		while (key_bits < 32 && (span >> key_bits) != 0u)
+			key_bits++;
+	}
+	caps.R_cap = R;
+	caps.R1_cap = R1;
+	caps.depth_passes = passes_for_bits(key_bits);
 	state->num_rendered = (int)R;
+	raise_marks(key, R, R1, key_bits);
+	return enqueue_binning_and_blend(c, caps, nullptr, nullptr);
+}
 
-	// Remaining passes of the depth sort.  Visible keys lie in [key_min, key_max]; subtracting a bias
-	// that is a multiple of 256 keeps the first pass's digit, preserves order and ties, and leaves only
-	// bit_length(key_max - bias) significant bits (23-24 for a scene a few units deep instead of 32).
-	// `order` ends up holding the V visible ids.  A visible Gaussian cannot carry the culled marker as
-	// its depth bits: 0xFFFFFFFF is a NaN pattern the GPU's arithmetic never produces (its NaN is
-	// 0x7FFFFFFF).
-	if (V > 0) {
-		const uint32_t bias = key_min <= key_max ? (key_min & ~0xFFu) : 0u;
-		const uint32_t span = key_min <= key_max ? key_max - bias : 0u;
-		int nbits = 8;
-		while (nbits < 32 && (span >> nbits) != 0u)
-			nbits++;
-		const int rest = nbits > 8 ? nbits - 8 : 1;
-		const int passes = (rest + 7) / 8;
-		const int base_bits = rest / passes, extra = rest % passes;
-		uint32_t *tmp_keys = nullptr, *tmp_vals = nullptr;
-		sort_tmp_buffers(depth_sort_scratch, (size_t)P, &tmp_keys, &tmp_vals);
-		const uint32_t* kin = first_keys;
-		const uint32_t* vin = first_vals;
-		int shift = 8;
-		for (int p = 0; p < passes; p++) {
-			const int bits = base_bits + (p < extra ? 1 : 0);
-			const bool to_out = ((passes - 1 - p) & 1) == 0;
-			uint32_t* ko = to_out ? sorted_depth : tmp_keys;
-			uint32_t* vo = to_out ? order : tmp_vals;
-			BRS_STAGE(BRS_STAGE_DEPTH_SORT, sort_pass(kin, vin, ko, vo, (size_t)V, bias, shift, bits, depth_sort_scratch, stream),
-			          debug, stream);
-			kin = ko;
-			vin = vo;
-			shift += bits;
-		}
+void brs_forward_stats(long long* out, int reset)
+{
+	for (int i = 0; i < 4; i++) {
+		if (out)
+			out[i] = t_fwd_stats[i];
+		if (reset)
+			t_fwd_stats[i] = 0;
 	}
+}
 
-	char* binning = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_BINNING, binning_bytes(R)));
-	if (binning == nullptr)
-		return BRS_ERR_ALLOC;
-	state->binning = binning;
-	state->binning_bytes = binning_bytes(R);
-	uint32_t* point_list = reinterpret_cast<uint32_t*>(binning);
+void brs_reset_marks(void)
+{
+	std::lock_guard<std::mutex> lock(g_marks_mutex);
+	g_marks.clear();
+}
 
-	if (grid_x * grid_y > 0) {
-		char* scratch2 = static_cast<char*>(alloc(alloc_ctx, BRS_BUF_SCRATCH, instance_scratch_bytes(P, R1, grid_x, grid_y)));
-		if (scratch2 == nullptr)
-			return BRS_ERR_ALLOC;
-		const size_t rb = align_up(sizeof(uint32_t) * (size_t)R1, 256);
-		uint32_t* cell_keys = reinterpret_cast<uint32_t*>(scratch2);
-		uint32_t* cell_ids = reinterpret_cast<uint32_t*>(scratch2 + rb);
-		uint32_t* sorted_keys = reinterpret_cast<uint32_t*>(scratch2 + 2 * rb);
-		uint32_t* coarse_list = reinterpret_cast<uint32_t*>(scratch2 + 3 * rb);
-		char* sort_scratch = scratch2 + 4 * rb;
-		char* emit_scratch = sort_scratch + sort_scratch_bytes(R1);
-		char* fine_scratch = emit_scratch + emit_scratch_bytes(P);
-		const uint32_t ns_x = supertiles(grid_x), ns = ns_x * supertiles(grid_y);
-
-		if (R1 > 0) {
-			BRS_STAGE(BRS_STAGE_COARSE_EMIT,
-			          launch_emit(order, rect, (size_t)V, ST_SHIFT, ns_x, cell_keys, cell_ids, (size_t)R1, emit_scratch,
-			                      stream),
-			          debug, stream);
-			BRS_STAGE(BRS_STAGE_COARSE_SORT,
-			          sort_pairs(cell_keys, cell_ids, sorted_keys, coarse_list, (size_t)R1, 0, tile_bits(ns), sort_scratch,
-			                     stream),
-			          debug, stream);
-		}
-		// also writes the (0,0) ranges of empty tiles (reference: cudaMemset, rasterizer_impl.cu:311)
-		BRS_STAGE(BRS_STAGE_FINE_BIN,
-		          launch_fine_binning(sorted_keys, coarse_list, (size_t)R1, rect, grid_x, grid_y, point_list, ranges,
-		                              fine_scratch, stream),
-		          debug, stream);
-	}
-
-	BlendFwdArgs ba{};
-	ba.ranges = ranges;
-	ba.point_list = point_list;
-	ba.records = records;
-	ba.bg = view->bg;
-	ba.W = W;
-	ba.H = H;
-	ba.grid_x = grid_x;
-	ba.grid_y = grid_y;
-	ba.final_T = final_T;
-	ba.n_contrib = n_contrib;
-	ba.out_color = out_color;
-	ba.out_depth = out_depth;
-	Companion comp;
-	if (!debug && companion_for(stream, comp)) {
-		BRS_CUDA(cudaEventRecord(comp.before, stream));
-		BRS_CUDA(cudaStreamWaitEvent(comp.stream, comp.before, 0));
-		BRS_CUDA(launch_blend_forward(ba, comp.stream));
-		BRS_CUDA(cudaEventRecord(comp.after, comp.stream));
-		BRS_CUDA(cudaStreamWaitEvent(stream, comp.after, 0));
-	} else {
-		BRS_STAGE(BRS_STAGE_BLEND_FWD, launch_blend_forward(ba, stream), debug, stream);
-	}
-	return BRS_OK;
+void brs_note_counts(int P, int image_width, int image_height, const uint32_t* report)
+{
+	int dev = 0;
+	if (report == nullptr || cudaGetDevice(&dev) != cudaSuccess)
+		return;
+	raise_marks(MarksKey{dev, P, image_width, image_height}, report[HDR_R], report[HDR_R1], report[HDR_KEY_BITS]);
 }
 
 int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii, const brs_fwd_state* state,
@@ -676,8 +814,10 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 	const GeomLayout gl = geom_layout(P);
 	const ImageLayout il = image_layout(W, H);
 	const int R = state->num_rendered;
+	// R == -1: a deferred forward, whose instance count never reached the host (brs_fwd_options)
 	if (state->geom == nullptr || state->image == nullptr || state->geom_bytes < gl.total ||
-	    state->image_bytes < il.total || R < 0 || (R > 0 && (state->binning == nullptr || state->binning_bytes < binning_bytes(R))))
+	    state->image_bytes < il.total || R < -1 || (R > 0 && (state->binning == nullptr || state->binning_bytes < binning_bytes(R))) ||
+	    (R == -1 && state->binning == nullptr))
 		return BRS_ERR_STATE;
 	if ((size_t)W * H > 0 && dL_dout_color == nullptr)
 		return BRS_ERR_INVALID_ARG;
@@ -695,7 +835,7 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 		return BRS_ERR_ALLOC;
 	BRS_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * ACCUM_STRIDE * (size_t)P, stream));
 
-	if (R > 0 && grid_x * grid_y > 0) {
+	if (R != 0 && grid_x * grid_y > 0) {
 		BlendBwdArgs bb{};
 		bb.ranges = reinterpret_cast<const uint2*>(image + il.ranges);
 		bb.point_list = reinterpret_cast<const uint32_t*>(state->binning);

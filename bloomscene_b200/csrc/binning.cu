@@ -6,33 +6,43 @@
 // reference's emission order yields — is produced here without ever sorting R-sized arrays:
 //
 //   1. stable sort of the P Gaussians by depth bits (u32 key, value = id; culled ones carry the
-//      key 0xFFFFFFFF, emit nothing, and may land anywhere)                    -> `order`
+//      key 0xFFFFFFFF and are dropped by the first pass)                               -> `order`
 //   2. COARSE level: one fused kernel scans supertiles-per-Gaussian in depth order (decoupled
-//      look-back, 32 predecessors per poll) and emits (supertile id, Gaussian id) instances, a
-//      supertile being 8x8 tiles; R1 ~ 1.3 V of them.  One stable radix pass on the supertile id
-//      (<= 8 bits up to 2048x2048 pixels) turns that into per-supertile lists in depth order.
-//   3. FINE level: every supertile list is cut into slices of 128 entries, one warp per slice.
+//      look-back, 32 predecessors per poll), emits (supertile id, Gaussian id) instances — a
+//      supertile being 8x8 tiles; R1 ~ 1.3 V of them — and histograms the supertile ids; its last
+//      CTA turns the histogram into the per-supertile list ranges and the slice plan of the fine
+//      level.  One stable radix pass on the supertile id (two above 256 supertiles) turns the
+//      instances into per-supertile lists in depth order.
+//   3. FINE level: every supertile list is cut into slices of 64 entries, one warp per slice.
 //      count  : per slice, how many entries cover each of the supertile's 64 tiles (lane = tile owner,
 //               entries broadcast one by one in list order)
-//      scan   : per (supertile, tile) exclusive prefix over the slices; then one exclusive scan over
-//               all tile ids gives every tile's start in `point_list` and the tile `ranges`
-//               (reference identifyTileRanges, rasterizer_impl.cu:116-138: empty tiles stay (0,0))
+//      scan   : per (supertile, tile) exclusive prefix over the slices; the last CTA to finish scans
+//               the per-tile totals in tile-id order, which gives every tile's start in `point_list`
+//               and the tile `ranges` (reference identifyTileRanges, rasterizer_impl.cu:116-138:
+//               empty tiles stay (0,0))
 //      scatter: the count loop again; every tile owner appends the ids covering its tile at its running
 //               position, so ids are written straight to their final place in stable order.
 //
 // Because (1) is stable in id, (2) is stable, and slices / lanes are walked in list order, instances
 // inside a tile end up ordered by (depth bits, id): exactly the reference's sorted `point_list`.
-// Traffic is ~70 P + 16 R1 + 4 R bytes instead of the reference's 152 R.
+// Traffic is ~60 P + 16 R1 + 4 R bytes instead of the reference's 152 R.
 //
-// The radix sort is hand-written.  Each pass over one digit is three kernels:
-//   upsweep   : per 2048-key tile, digit counts (warp match_any + shared atomics)  -> table[digit][tile]
-//   scan      : one block per digit, exclusive scan along the tiles + digit totals
-//   downsweep : per tile, stable ranks (match_any + shared atomics returning the old value, so the
-//               16 keys of a thread are in flight together), scatter through shared memory so
-//               global writes are coalesced per digit run.
-// A single-pass chained scan ("onesweep") was measured first: with ~600 tiles resident at once the
-// first wave spends ~100 us per pass polling unpublished predecessors on this GPU, far more than
-// the extra 4 bytes/key the upsweep reads (see profiles/).
+// NO HOST KNOWLEDGE OF COUNTS.  Every kernel here takes the CAPACITIES of its arrays from the host
+// (P, R1_cap, R_cap) and reads the actual counts (V visible Gaussians, R1 supertile instances, the
+// depth-key range) from the geometry header on the device.  Grids are sized by capacity; CTAs whose
+// work unit lies beyond the actual count leave at once.  Writes are guarded by the capacities, so a
+// forward whose capacities turn out too small is memory-safe; it raises the overflow word of the
+// header and the caller runs it again with the exact sizes (api.cu).
+//
+// The radix sort is hand-written, one kernel per digit ("onesweep"): a histogram kernel counts all
+// digits of all passes in one read of the keys; a pass then ranks a 4096-key tile (warp match_any +
+// shared atomics), publishes the tile's digit counts, finds its global offsets by decoupled look-back
+// over the predecessor tiles' published counts (tile ids are handed out by an atomic ticket, so a CTA
+// only ever waits for CTAs that are already running) and scatters through shared memory so that global
+// writes are coalesced per digit run.  Measured against cub::DeviceRadixSort::SortPairs on the same
+// problem: tools/sort_vs_cub.cu, profiles/.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -40,15 +50,14 @@ namespace brs {
 
 namespace {
 
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 8;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 2048 pairs per tile (smaller tiles = more CTAs in flight: the passes are latency-bound chains of MATCH/ATOMS)
-constexpr int RADIX_MAX = 256;
-constexpr int MAX_PASSES = 4;
+constexpr int OS_THREADS = 256;
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_ITEMS = 16;
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS; // 4096 pairs per tile
+constexpr int RADIX = 256;
 
-constexpr uint32_t FLAG_LOCAL = 1u << 30; // (emit scan) block-local count published
-constexpr uint32_t FLAG_INCL = 2u << 30;  // (emit scan) inclusive prefix published
+constexpr uint32_t FLAG_LOCAL = 1u << 30; // tile-local count published
+constexpr uint32_t FLAG_INCL = 2u << 30;  // inclusive prefix published
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
 
@@ -64,7 +73,7 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v)
 }
 
 // Exclusive scan of one value per thread over a 256-thread block; also returns the block total.
-// s_warp must hold SORT_WARPS uint32.  Contains two __syncthreads.
+// s_warp must hold 8 uint32.  Contains two __syncthreads.
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp, uint32_t& total)
 {
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -80,7 +89,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 	__syncthreads();
 	uint32_t warp_off = 0, tot = 0;
 #pragma unroll
-	for (int w = 0; w < SORT_WARPS; w++) {
+	for (int w = 0; w < OS_WARPS; w++) {
 		const uint32_t c = s_warp[w];
 		if ((uint32_t)w < warp)
 			warp_off += c;
@@ -91,101 +100,151 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 	return warp_off + incl - v;
 }
 
-// ---- upsweep: digit counts of one tile ------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS)
-    upsweep_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t bias, int shift, int bits, uint32_t tiles,
-                   uint32_t* __restrict__ table, uint32_t drop_key, int drop)
+// The depth sort's key transform lives on the device: bias = (min visible key) & ~255, so that the
+// first digit (key bits 0..7) does not depend on it.  hdr[2] holds max(~key) = ~min.
+__device__ __forceinline__ uint32_t depth_bias(const uint32_t* hdr)
 {
-	__shared__ uint32_t s_cnt[RADIX_MAX];
-	const uint32_t tid = threadIdx.x, lane = tid & 31;
-	const uint32_t radix = 1u << bits, mask = radix - 1u;
-	s_cnt[tid] = 0;
-	__syncthreads();
-	const uint32_t tile = blockIdx.x;
-	const uint32_t base = tile * SORT_TILE;
-	const uint32_t valid_count = min((uint32_t)SORT_TILE, n - base);
-	uint32_t key[SORT_ITEMS];
-#pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++) {
-		const uint32_t li = tid + i * SORT_THREADS;
-		key[i] = (li < valid_count) ? __ldg(keys + base + li) : 0xffffffffu;
-	}
-#pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++) {
-		const bool valid = (tid + i * SORT_THREADS) < valid_count && !(drop && key[i] == drop_key);
-		const uint32_t d = ((key[i] - bias) >> shift) & mask;
-		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
-		if (valid && (uint32_t)(__ffs(peers) - 1) == lane)
-			atomicAdd(s_cnt + d, (uint32_t)__popc(peers));
-	}
-	__syncthreads();
-	if (tid < radix)
-		table[(size_t)tid * tiles + tile] = s_cnt[tid];
+	const uint32_t V = hdr[HDR_V];
+	return V ? ((~hdr[HDR_KEY_INVMIN]) & ~0xFFu) : 0u;
 }
 
-// ---- scan: per digit, exclusive prefix over the tiles (in place) + digit total --------------------
-__global__ void __launch_bounds__(SORT_THREADS) scan_kernel(uint32_t* __restrict__ table, uint32_t tiles,
-                                                           uint32_t* __restrict__ totals)
+// ---- histogram of every digit of every pass, one read of the keys -----------------------------------
+struct HistArgs {
+	const uint32_t* keys;
+	uint32_t n;              // capacity
+	const uint32_t* n_ptr;   // actual count on the device (nullptr: n)
+	const uint32_t* hdr;     // geometry header (depth sort: bias + overflow bookkeeping) or nullptr
+	uint32_t* hdr_out;       // same header, writable (overflow word), or nullptr
+	int passes;
+	int shift[4], bits[4];
+	int drop;                // keys equal to DEPTH_KEY_CULLED do not take part
+	uint32_t R_cap, R1_cap;  // for the overflow word (depth sort only)
+	uint32_t* hist;          // [passes][RADIX], pre-zeroed
+};
+
+__global__ void __launch_bounds__(OS_THREADS) radix_hist_kernel(HistArgs a)
 {
-	__shared__ uint32_t s_warp[SORT_WARPS];
-	uint32_t* row = table + (size_t)blockIdx.x * tiles;
-	uint32_t carry = 0;
-	for (uint32_t t0 = 0; t0 < tiles; t0 += SORT_THREADS) {
-		const uint32_t t = t0 + threadIdx.x;
-		const uint32_t v = (t < tiles) ? row[t] : 0u;
-		uint32_t total;
-		const uint32_t ex = block_exclusive_scan_256(v, s_warp, total);
-		if (t < tiles)
-			row[t] = carry + ex;
-		carry += total;
+	__shared__ uint32_t s_hist[4][RADIX];
+	const uint32_t tid = threadIdx.x;
+	for (int i = tid; i < 4 * RADIX; i += OS_THREADS)
+		(&s_hist[0][0])[i] = 0;
+	__syncthreads();
+	const uint32_t n = a.n_ptr ? min(a.n, __ldg(a.n_ptr)) : a.n;
+	const uint32_t bias = a.hdr ? depth_bias(a.hdr) : 0u;
+	if (a.hdr_out != nullptr && blockIdx.x == 0 && tid == 0) {
+		// overflow bookkeeping of the optimistic forward: do the capacities and the planned key bits hold?
+		const uint32_t V = a.hdr[HDR_V];
+		uint32_t nbits = 8;
+		if (V) {
+			const uint32_t span = a.hdr[HDR_KEY_MAX] - bias;
+			while (nbits < 32 && (span >> nbits) != 0u)
+				nbits++;
+		}
+		int planned = 0;
+		for (int p = 0; p < a.passes; p++)
+			planned = max(planned, a.shift[p] + a.bits[p]);
+		uint32_t flags = 0;
+		if (a.hdr[HDR_R] > a.R_cap)
+			flags |= 1u;
+		if (a.hdr[HDR_R1] > a.R1_cap)
+			flags |= 2u;
+		if ((int)nbits > planned)
+			flags |= 4u;
+		a.hdr_out[HDR_OVERFLOW] = flags;
+		a.hdr_out[HDR_KEY_BITS] = nbits;
 	}
-	if (threadIdx.x == 0)
-		totals[blockIdx.x] = carry;
+	for (uint32_t i = blockIdx.x * OS_THREADS + tid; i < n; i += gridDim.x * OS_THREADS) {
+		const uint32_t key = __ldg(a.keys + i);
+		if (a.drop && key == DEPTH_KEY_CULLED)
+			continue;
+		const uint32_t k = key - bias;
+#pragma unroll
+		for (int p = 0; p < 4; p++)
+			if (p < a.passes)
+				atomicAdd(&s_hist[p][(k >> a.shift[p]) & ((1u << a.bits[p]) - 1u)], 1u);
+	}
+	__syncthreads();
+	for (int i = tid; i < a.passes * RADIX; i += OS_THREADS) {
+		const uint32_t c = (&s_hist[0][0])[i];
+		if (c)
+			atomicAdd(a.hist + i, c);
+	}
 }
 
-// ---- downsweep: stable scatter of one tile --------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS)
-    downsweep_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint32_t* __restrict__ kout,
-                     uint32_t* __restrict__ vout, uint32_t n, uint32_t bias, int shift, int bits, uint32_t tiles,
-                     const uint32_t* __restrict__ table, const uint32_t* __restrict__ totals, uint32_t drop_key, int drop)
+// ---- one radix pass ---------------------------------------------------------------------------------
+struct PassArgs {
+	const uint32_t* kin;
+	const uint32_t* vin;     // nullptr: iota
+	uint32_t* kout;          // nullptr: keys are not written (nobody reads them after the last pass)
+	uint32_t* vout;
+	uint32_t n;              // capacity
+	const uint32_t* n_ptr;   // actual count (nullptr: n)
+	const uint32_t* hdr;     // depth sort: bias from the header; nullptr: bias 0
+	int shift, bits;
+	int drop;
+	const uint32_t* hist;    // [RADIX] digit totals of this pass, or (fold_n > 0) totals per full key value
+	uint32_t fold_n;         // > 0: hist holds one count per key value 0..fold_n-1; fold it onto this pass's digit
+	uint32_t* status;        // [tiles][RADIX], pre-zeroed
+	uint32_t* ticket;        // pre-zeroed
+};
+
+__global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(PassArgs a)
 {
-	__shared__ uint32_t s_cnt[SORT_WARPS][RADIX_MAX];
-	__shared__ uint32_t s_keys[SORT_TILE];
-	__shared__ uint32_t s_vals[SORT_TILE];
-	__shared__ uint32_t s_digit_start[RADIX_MAX];
-	__shared__ uint32_t s_goff[RADIX_MAX];
-	__shared__ uint32_t s_warp[SORT_WARPS];
+	__shared__ uint32_t s_cnt[OS_WARPS][RADIX];
+	__shared__ uint32_t s_keys[OS_TILE];
+	__shared__ uint32_t s_vals[OS_TILE];
+	__shared__ uint32_t s_digit_start[RADIX];
+	__shared__ uint32_t s_goff[RADIX];
+	__shared__ uint32_t s_fold[RADIX];
+	__shared__ uint32_t s_warp[OS_WARPS];
+	__shared__ uint32_t s_tile;
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t radix = 1u << bits, mask = radix - 1u;
-	for (int i = tid; i < SORT_WARPS * RADIX_MAX; i += SORT_THREADS)
+	const uint32_t radix = 1u << a.bits, mask = radix - 1u;
+	if (tid == 0)
+		s_tile = atomicAdd(a.ticket, 1u);
+	for (int i = tid; i < OS_WARPS * RADIX; i += OS_THREADS)
 		(&s_cnt[0][0])[i] = 0;
+	s_fold[tid] = 0;
 	__syncthreads();
-	const uint32_t tile = blockIdx.x;
-	const uint32_t base = tile * SORT_TILE;
-	const uint32_t valid_count = min((uint32_t)SORT_TILE, n - base);
+	const uint32_t n = a.n_ptr ? min(a.n, __ldg(a.n_ptr)) : a.n;
+	const uint32_t tiles = (n + OS_TILE - 1) / OS_TILE;
+	const uint32_t tile = s_tile;
+	if (tile >= tiles)
+		return;
+	const uint32_t bias = a.hdr ? depth_bias(a.hdr) : 0u;
+	const uint32_t base = tile * OS_TILE;
+	const uint32_t valid_count = min((uint32_t)OS_TILE, n - base);
 
 	// load keys (warp-striped: coalesced, and rank order == index order)
-	uint32_t key[SORT_ITEMS], rank[SORT_ITEMS];
-	const uint32_t wbase = warp * (32 * SORT_ITEMS) + lane;
+	uint32_t key[OS_ITEMS], rank[OS_ITEMS];
+	const uint32_t wbase = warp * (32 * OS_ITEMS) + lane;
 #pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++) {
+	for (int i = 0; i < OS_ITEMS; i++) {
 		const uint32_t li = wbase + i * 32;
-		key[i] = (li < valid_count) ? __ldg(kin + base + li) : 0xffffffffu;
+		key[i] = (li < valid_count) ? __ldg(a.kin + base + li) : 0xffffffffu;
 	}
-	// global offsets of this tile's digits (independent of the ranking below)
-	const uint32_t tile_excl = (tid < radix) ? __ldg(table + (size_t)tid * tiles + tile) : 0u;
-	const uint32_t digit_total = (tid < radix) ? __ldg(totals + tid) : 0u;
+	// digit totals over the whole input (independent of the ranking below)
+	uint32_t digit_total = 0;
+	if (a.fold_n) {
+		for (uint32_t s = tid; s < a.fold_n; s += OS_THREADS) {
+			const uint32_t c = ld_relaxed(a.hist + s);
+			if (c)
+				atomicAdd(&s_fold[(s >> a.shift) & mask], c);
+		}
+	} else if (tid < radix) {
+		digit_total = ld_relaxed(a.hist + tid);
+	}
 
 	// rank inside the warp (stable).  match_any groups equal digits; the group's first lane bumps the
 	// warp-private counter with a shared-memory atomic that returns the old value.  Same-address
-	// atomics of one warp complete in program order, so no barrier is needed and all SORT_ITEMS
+	// atomics of one warp complete in program order, so no barrier is needed and all OS_ITEMS
 	// chains (MATCH -> ATOMS -> SHFL) overlap.
 	uint32_t* my_cnt = s_cnt[warp];
 #pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++) {
-		const bool valid = (wbase + i * 32) < valid_count && !(drop && key[i] == drop_key);
-		const uint32_t d = ((key[i] - bias) >> shift) & mask;
+	for (int i = 0; i < OS_ITEMS; i++) {
+		const bool valid = (wbase + i * 32) < valid_count && !(a.drop && key[i] == DEPTH_KEY_CULLED);
+		const uint32_t d = ((key[i] - bias) >> a.shift) & mask;
 		const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
 		const int leader = __ffs(peers) - 1;
 		uint32_t old = 0;
@@ -195,143 +254,83 @@ __global__ void __launch_bounds__(SORT_THREADS)
 		rank[i] = old + __popc(peers & lanemask_lt());
 	}
 	__syncthreads();
+	if (a.fold_n && tid < radix)
+		digit_total = s_fold[tid];
 
-	// per digit: exclusive offsets of the warps, tile total
+	// per digit: exclusive offsets of the warps, tile total; publish the tile's digit counts at once so
+	// that successors can start summing them
 	uint32_t total = 0;
 	if (tid < radix) {
 #pragma unroll
-		for (int w = 0; w < SORT_WARPS; w++) {
+		for (int w = 0; w < OS_WARPS; w++) {
 			const uint32_t c = s_cnt[w][tid];
 			s_cnt[w][tid] = total;
 			total += c;
 		}
+		st_relaxed(a.status + (size_t)tile * RADIX + tid, (tile == 0 ? FLAG_INCL : FLAG_LOCAL) | total);
 	}
 	uint32_t dummy, kept; // kept = keys of this tile that take part (all valid ones unless `drop`)
 	const uint32_t digit_start = block_exclusive_scan_256(total, s_warp, kept);
 	const uint32_t bin_base = block_exclusive_scan_256(digit_total, s_warp, dummy);
-	if (tid < radix) {
+	if (tid < radix)
 		s_digit_start[tid] = digit_start;
-		s_goff[tid] = bin_base + tile_excl - digit_start; // global position = s_goff[d] + position in tile
-	}
 	__syncthreads();
 
-	// scatter into shared memory in sorted-by-digit order (values are fetched only now)
+	// scatter into shared memory in sorted-by-digit order (values are fetched only now); this also
+	// gives the predecessors time to publish
 #pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++) {
+	for (int i = 0; i < OS_ITEMS; i++) {
 		const uint32_t li = wbase + i * 32;
-		if (li < valid_count && !(drop && key[i] == drop_key)) {
-			const uint32_t d = ((key[i] - bias) >> shift) & mask;
+		if (li < valid_count && !(a.drop && key[i] == DEPTH_KEY_CULLED)) {
+			const uint32_t d = ((key[i] - bias) >> a.shift) & mask;
 			const uint32_t pos = s_digit_start[d] + s_cnt[warp][d] + rank[i];
 			s_keys[pos] = key[i];
-			s_vals[pos] = vin ? __ldg(vin + base + li) : base + li;
+			s_vals[pos] = a.vin ? __ldg(a.vin + base + li) : base + li;
 		}
+	}
+
+	// decoupled look-back: thread d sums digit d over the predecessor tiles until it meets an inclusive prefix
+	if (tid < radix) {
+		uint32_t excl = 0;
+		int p = (int)tile - 1;
+		while (p >= 0) {
+			const uint32_t v = ld_relaxed(a.status + (size_t)p * RADIX + tid);
+			const uint32_t f = v & FLAG_MASK;
+			if (f == 0)
+				continue; // not published yet (that tile holds an earlier ticket: it is running)
+			excl += v & VALUE_MASK;
+			if (f == FLAG_INCL)
+				break;
+			p--;
+		}
+		if (tile > 0)
+			st_relaxed(a.status + (size_t)tile * RADIX + tid, FLAG_INCL | (excl + total));
+		s_goff[tid] = bin_base + excl - digit_start; // global position = s_goff[d] + position in tile
 	}
 	__syncthreads();
 
 	// coalesced write-out: consecutive threads hold consecutive positions of a digit run
 #pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++) {
-		const uint32_t j = tid + i * SORT_THREADS;
+	for (int i = 0; i < OS_ITEMS; i++) {
+		const uint32_t j = tid + i * OS_THREADS;
 		if (j < kept) {
 			const uint32_t k = s_keys[j];
-			const uint32_t g = s_goff[((k - bias) >> shift) & mask] + j;
-			kout[g] = k;
-			vout[g] = s_vals[j];
+			const uint32_t g = s_goff[((k - bias) >> a.shift) & mask] + j;
+			if (a.kout)
+				a.kout[g] = k;
+			a.vout[g] = s_vals[j];
 		}
 	}
 }
 
-struct SortScratch {
-	uint32_t* table;  // [RADIX_MAX][tiles] (reused by every pass)
-	uint32_t* totals; // [RADIX_MAX]
-	uint32_t* tmp_keys;
-	uint32_t* tmp_vals;
-	size_t total_bytes;
-};
+inline uint32_t sort_tiles(size_t n) { return (uint32_t)((n + OS_TILE - 1) / OS_TILE); }
 
-SortScratch carve_sort_scratch(void* scratch, size_t n)
-{
-	SortScratch s{};
-	const size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-	char* p = static_cast<char*>(scratch);
-	size_t off = 0;
-	s.table = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * RADIX_MAX * (tiles ? tiles : 1), 256);
-	s.totals = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * RADIX_MAX, 256);
-	s.tmp_keys = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * n, 256);
-	s.tmp_vals = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * n, 256);
-	s.total_bytes = off;
-	return s;
-}
-
-} // namespace
-
-size_t sort_scratch_bytes(size_t n) { return carve_sort_scratch(nullptr, n).total_bytes; }
-
-void sort_tmp_buffers(void* scratch, size_t n, uint32_t** tmp_keys, uint32_t** tmp_vals)
-{
-	SortScratch s = carve_sort_scratch(scratch, n);
-	*tmp_keys = s.tmp_keys;
-	*tmp_vals = s.tmp_vals;
-}
-
-cudaError_t sort_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout, size_t n, uint32_t bias,
-                      int shift, int bits, void* scratch, cudaStream_t stream, bool drop, uint32_t drop_key)
-{
-	if (n == 0)
-		return cudaSuccess;
-	SortScratch s = carve_sort_scratch(scratch, n);
-	const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
-	upsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, (uint32_t)n, bias, shift, bits, tiles, s.table, drop_key,
-	                                                   drop ? 1 : 0);
-	scan_kernel<<<1u << bits, SORT_THREADS, 0, stream>>>(s.table, tiles, s.totals);
-	downsweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, (uint32_t)n, bias, shift, bits, tiles,
-	                                                     s.table, s.totals, drop_key, drop ? 1 : 0);
-	count_launch();
-	count_launch();
-	count_launch();
-	return cudaGetLastError();
-}
-
-cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                       size_t n, int begin_bit, int end_bit, void* scratch, cudaStream_t stream)
-{
-	if (n == 0)
-		return cudaSuccess;
-	int nbits = end_bit - begin_bit;
-	if (nbits < 1)
-		nbits = 1;
-	const int passes = (nbits + 7) / 8;
-	const int base_bits = nbits / passes, extra = nbits % passes;
-	SortScratch s = carve_sort_scratch(scratch, n);
-	const uint32_t* kin = keys_in;
-	const uint32_t* vin = vals_in;
-	int shift = begin_bit;
-	for (int p = 0; p < passes; p++) {
-		const int bits = base_bits + (p < extra ? 1 : 0);
-		const bool to_out = ((passes - 1 - p) & 1) == 0;
-		uint32_t* ko = to_out ? keys_out : s.tmp_keys;
-		uint32_t* vo = to_out ? vals_out : s.tmp_vals;
-		cudaError_t e = sort_pass(kin, vin, ko, vo, n, 0u, shift, bits, scratch, stream);
-		if (e != cudaSuccess)
-			return e;
-		kin = ko;
-		vin = vo;
-		shift += bits;
-	}
-	return cudaGetLastError();
-}
-
-// ---- fused scan + emission ------------------------------------------------------------------------
-
-namespace {
+// ---- fused scan + emission --------------------------------------------------------------------------
 
 constexpr int EMIT_THREADS = 256;
 constexpr int EMIT_ITEMS = 4;
 constexpr int EMIT_TILE = EMIT_THREADS * EMIT_ITEMS; // Gaussians per block
+constexpr int CELL_HIST_MAX = 2048;                  // supertile ids histogrammed in shared memory
 
 // Tile rectangle -> rectangle in cells of (1 << shift) tiles; an empty rectangle stays empty.
 __device__ __forceinline__ uint2 coarsen_rect(uint2 r, uint32_t shift)
@@ -342,22 +341,72 @@ __device__ __forceinline__ uint2 coarsen_rect(uint2 r, uint32_t shift)
 	return make_uint2((x0 >> shift) | ((((x1 - 1) >> shift) + 1) << 16), (y0 >> shift) | ((((y1 - 1) >> shift) + 1) << 16));
 }
 
-__global__ void __launch_bounds__(EMIT_THREADS)
-    emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rect, uint32_t P, uint32_t shift,
-                uint32_t grid_x, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ inst_ids, uint32_t R,
-                uint32_t* status, uint32_t* ticket)
+struct EmitArgs {
+	const uint32_t* order;   // ids in depth order
+	const uint2* rect;
+	const uint32_t* hdr;     // V = hdr[HDR_V]
+	uint32_t shift, ns_x, ns;
+	uint32_t* cell_keys;     // [R1_cap]
+	uint32_t* cell_ids;      // [R1_cap]
+	uint32_t R1_cap;
+	uint32_t* status;        // [blocks], pre-zeroed
+	uint32_t* ticket;        // pre-zeroed
+	uint32_t* done;          // pre-zeroed
+	uint32_t* cell_count;    // [ns], pre-zeroed
+	uint2* coarse_ranges;    // [ns]      (written by the last CTA)
+	uint32_t* slice_base;    // [ns + 1]  (written by the last CTA)
+	uint32_t* n_instances;   // min(R1, R1_cap) (written by the last CTA)
+};
+
+// The last CTA of the emission: per-supertile totals -> list ranges in the sorted instance array and the
+// fine level's slice plan (ceil(n_s / FINE_SLICE) slices per supertile, exclusive scan).
+__device__ void emit_finalize(const EmitArgs& a, uint32_t* s_warp)
+{
+	uint32_t carry_inst = 0, carry_slices = 0;
+	for (uint32_t s0 = 0; s0 < a.ns; s0 += EMIT_THREADS) {
+		const uint32_t s = s0 + threadIdx.x;
+		const uint32_t v = (s < a.ns) ? ld_relaxed(a.cell_count + s) : 0u;
+		uint32_t tot_i, tot_s;
+		const uint32_t ex_i = block_exclusive_scan_256(v, s_warp, tot_i);
+		const uint32_t ex_s = block_exclusive_scan_256((v + FINE_SLICE - 1) / FINE_SLICE, s_warp, tot_s);
+		if (s < a.ns) {
+			a.coarse_ranges[s] = make_uint2(carry_inst + ex_i, carry_inst + ex_i + v);
+			a.slice_base[s] = carry_slices + ex_s;
+		}
+		carry_inst += tot_i;
+		carry_slices += tot_s;
+	}
+	if (threadIdx.x == 0) {
+		a.slice_base[a.ns] = carry_slices;
+		*a.n_instances = carry_inst;
+	}
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(EmitArgs a)
 {
 	__shared__ uint32_t s_incl[EMIT_TILE]; // inclusive instance offsets inside this block
 	__shared__ uint32_t s_id[EMIT_TILE];
 	__shared__ uint2 s_rect[EMIT_TILE];
-	__shared__ uint32_t s_warp[SORT_WARPS];
+	__shared__ uint32_t s_hist[CELL_HIST_MAX];
+	__shared__ uint32_t s_warp[OS_WARPS];
 	__shared__ uint32_t s_bcast[2];
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0)
-		s_bcast[0] = atomicAdd(ticket, 1u);
+		s_bcast[0] = atomicAdd(a.ticket, 1u);
+	const bool smem_hist = a.ns <= CELL_HIST_MAX;
+	if (smem_hist)
+		for (uint32_t i = tid; i < a.ns; i += EMIT_THREADS)
+			s_hist[i] = 0;
 	__syncthreads();
 	const uint32_t blk = s_bcast[0];
+	const uint32_t V = __ldg(a.hdr + HDR_V);
+	const uint32_t blocks = (V + EMIT_TILE - 1) / EMIT_TILE;
+	if (blk >= blocks) {
+		if (blocks == 0 && blk == 0)
+			emit_finalize(a, s_warp); // nothing visible: all lists are empty
+		return;
+	}
 	const uint32_t first = blk * EMIT_TILE + tid * EMIT_ITEMS;
 
 	uint32_t cnt[EMIT_ITEMS];
@@ -367,9 +416,9 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 		const uint32_t s = first + k;
 		uint32_t id = 0;
 		uint2 r = make_uint2(0u, 0u);
-		if (s < P) {
-			id = __ldg(order + s);
-			r = coarsen_rect(__ldg(rect + id), shift);
+		if (s < V) {
+			id = __ldg(a.order + s);
+			r = coarsen_rect(__ldg(a.rect + id), a.shift);
 		}
 		const uint32_t w = (r.x >> 16) - (r.x & 0xffffu);
 		const uint32_t hgt = (r.y >> 16) - (r.y & 0xffffu);
@@ -390,12 +439,12 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 	// 32 predecessors per poll
 	if (warp == 0) {
 		if (lane == 0)
-			st_relaxed(status + blk, (blk == 0 ? FLAG_INCL : FLAG_LOCAL) | block_total);
+			st_relaxed(a.status + blk, (blk == 0 ? FLAG_INCL : FLAG_LOCAL) | block_total);
 		uint32_t excl = 0;
 		int p = (int)blk - 1;
 		while (p >= 0) {
 			const int q = p - (int)lane;
-			const uint32_t v = (q >= 0) ? ld_relaxed(status + q) : FLAG_INCL;
+			const uint32_t v = (q >= 0) ? ld_relaxed(a.status + q) : FLAG_INCL;
 			const uint32_t f = v & FLAG_MASK;
 			const uint32_t not_ready = __ballot_sync(0xffffffffu, f == 0);
 			const uint32_t inclusive = __ballot_sync(0xffffffffu, f == FLAG_INCL);
@@ -413,7 +462,7 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 		}
 		if (lane == 0) {
 			if (blk > 0)
-				st_relaxed(status + blk, FLAG_INCL | (excl + block_total));
+				st_relaxed(a.status + blk, FLAG_INCL | (excl + block_total));
 			s_bcast[1] = excl;
 		}
 	}
@@ -436,91 +485,42 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 		const uint32_t k = j - (s_incl[lo] - w * hgt);
 		const uint32_t row = k / w;
 		const uint32_t g = gbase + j;
-		if (g < R) {
-			tile_keys[g] = (y0 + row) * grid_x + x0 + (k - row * w);
-			inst_ids[g] = s_id[lo];
+		if (g < a.R1_cap) { // beyond the capacity: dropped (the header's overflow word is raised, the caller re-runs)
+			const uint32_t cell = (y0 + row) * a.ns_x + x0 + (k - row * w);
+			a.cell_keys[g] = cell;
+			a.cell_ids[g] = s_id[lo];
+			if (smem_hist)
+				atomicAdd(&s_hist[cell], 1u);
+			else
+				atomicAdd(a.cell_count + cell, 1u);
 		}
 	}
-}
-
-__global__ void __launch_bounds__(256)
-    tile_ranges_kernel(const uint32_t* __restrict__ keys, uint32_t R, uint2* __restrict__ ranges)
-{
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= R)
-		return;
-	const uint32_t cur = __ldg(keys + i);
-	if (i == 0)
-		ranges[cur].x = 0;
-	else {
-		const uint32_t prev = __ldg(keys + i - 1);
-		if (cur != prev) {
-			ranges[prev].y = i;
-			ranges[cur].x = i;
+	__syncthreads();
+	if (smem_hist)
+		for (uint32_t i = tid; i < a.ns; i += EMIT_THREADS) {
+			const uint32_t c = s_hist[i];
+			if (c)
+				atomicAdd(a.cell_count + i, c);
 		}
+	// last CTA done -> finalize
+	__threadfence();
+	__syncthreads();
+	if (tid == 0)
+		s_bcast[0] = atomicAdd(a.done, 1u);
+	__syncthreads();
+	if (s_bcast[0] == blocks - 1) {
+		__threadfence();
+		emit_finalize(a, s_warp);
 	}
-	if (i == R - 1)
-		ranges[cur].y = R;
-}
-
-} // namespace
-
-size_t emit_scratch_bytes(size_t P)
-{
-	const size_t blocks = (P + EMIT_TILE - 1) / EMIT_TILE;
-	return align_up(256 + sizeof(uint32_t) * blocks, 256);
-}
-
-cudaError_t launch_emit(const uint32_t* order, const uint2* rect, size_t P, uint32_t shift, uint32_t grid_x,
-                        uint32_t* tile_keys, uint32_t* inst_ids, size_t R, void* scratch, cudaStream_t stream)
-{
-	if (P == 0)
-		return cudaSuccess;
-	const uint32_t blocks = (uint32_t)((P + EMIT_TILE - 1) / EMIT_TILE);
-	cudaError_t e = cudaMemsetAsync(scratch, 0, emit_scratch_bytes(P), stream);
-	if (e != cudaSuccess)
-		return e;
-	uint32_t* ticket = static_cast<uint32_t*>(scratch);
-	uint32_t* status = ticket + 64;
-	emit_kernel<<<blocks, EMIT_THREADS, 0, stream>>>(order, rect, (uint32_t)P, shift, grid_x, tile_keys, inst_ids,
-	                                                 (uint32_t)R, status, ticket);
-	count_launch();
-	return cudaGetLastError();
 }
 
 // ---- fine level: supertile lists -> per-tile lists --------------------------------------------------
-
-namespace {
 
 constexpr int FINE_WARPS = 8; // warps (= slices) per CTA of the count / scatter kernels
 
 __device__ __forceinline__ uint32_t spread4(uint32_t b) // bit i of b (i < 4) -> bit 8 i
 {
 	return (b * 0x00204081u) & 0x01010101u;
-}
-
-// Exclusive scan of ceil(n_s / FINE_SLICE) over the supertiles -> slice_base[0..ns]; also copies the
-// list starts.  One CTA (ns is a few hundred).
-__global__ void __launch_bounds__(SORT_THREADS)
-    fine_plan_kernel(const uint2* __restrict__ coarse_ranges, uint32_t ns, uint32_t* __restrict__ slice_base)
-{
-	__shared__ uint32_t s_warp[SORT_WARPS];
-	uint32_t carry = 0;
-	for (uint32_t s0 = 0; s0 < ns; s0 += SORT_THREADS) {
-		const uint32_t s = s0 + threadIdx.x;
-		uint32_t v = 0;
-		if (s < ns) {
-			const uint2 r = coarse_ranges[s];
-			v = (r.y - r.x + FINE_SLICE - 1) / FINE_SLICE;
-		}
-		uint32_t total;
-		const uint32_t ex = block_exclusive_scan_256(v, s_warp, total);
-		if (s < ns)
-			slice_base[s] = carry + ex;
-		carry += total;
-	}
-	if (threadIdx.x == 0)
-		slice_base[ns] = carry;
 }
 
 // One warp per slice of <= FINE_SLICE consecutive entries of one supertile's list.  Entries are read 32
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32)
     fine_kernel(const uint32_t* __restrict__ coarse_list, const uint2* __restrict__ coarse_ranges,
                 const uint32_t* __restrict__ slice_base, const uint2* __restrict__ rect, uint32_t ns, uint32_t ns_x,
                 uint32_t grid_x, uint32_t grid_y, uint32_t* __restrict__ table, const uint32_t* __restrict__ tile_start,
-                uint32_t* __restrict__ point_list)
+                uint32_t* __restrict__ point_list, uint32_t R_cap)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t sl = blockIdx.x * FINE_WARPS + (threadIdx.x >> 5);
@@ -589,10 +589,16 @@ __global__ void __launch_bounds__(FINE_WARPS * 32)
 				const uint32_t mlo = __shfl_sync(0xffffffffu, lo, j);
 				const uint32_t mhi = __shfl_sync(0xffffffffu, hi, j);
 				const uint32_t idj = __shfl_sync(0xffffffffu, id, j);
-				if ((mlo >> lane) & 1u)
-					point_list[run0++] = idj;
-				if ((mhi >> lane) & 1u)
-					point_list[run1++] = idj;
+				if ((mlo >> lane) & 1u) {
+					if (run0 < R_cap)
+						point_list[run0] = idj;
+					run0++;
+				}
+				if ((mhi >> lane) & 1u) {
+					if (run1 < R_cap)
+						point_list[run1] = idj;
+					run1++;
+				}
 			}
 		} else {
 #pragma unroll 8
@@ -611,12 +617,18 @@ __global__ void __launch_bounds__(FINE_WARPS * 32)
 }
 
 // Per supertile (one CTA, 4 groups x 64 tiles): exclusive prefix of the slice counts along the
-// slices, in place, and the per-tile totals into tile_count[tile id].
+// slices, in place, and the per-tile totals into tile_count[tile id].  The last CTA to finish then
+// scans the per-tile totals in tile-id order -> tile_start, and the tile ranges (reference
+// identifyTileRanges: tiles without instances keep (0, 0)); ranges are clamped to the capacity of
+// `point_list` so that an overflowing forward stays memory-safe.
 __global__ void __launch_bounds__(256)
-    fine_scan_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slice_base, uint32_t ns_x,
-                     uint32_t grid_x, uint32_t grid_y, uint32_t* __restrict__ tile_count)
+    fine_scan_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slice_base, uint32_t ns_x, uint32_t grid_x,
+                     uint32_t grid_y, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_start,
+                     uint2* __restrict__ ranges, uint32_t R_cap, uint32_t* done)
 {
 	__shared__ uint32_t s_part[4][ST_TILES];
+	__shared__ uint32_t s_warp[OS_WARPS];
+	__shared__ uint32_t s_last;
 	const uint32_t st = blockIdx.x;
 	const uint32_t first = __ldg(slice_base + st), nsl = __ldg(slice_base + st + 1) - first;
 	const uint32_t t = threadIdx.x & 63, q = threadIdx.x >> 6;
@@ -646,141 +658,355 @@ __global__ void __launch_bounds__(256)
 	if (q == 0) {
 		const uint32_t x = ((st % ns_x) << ST_SHIFT) + (t & 7), y = ((st / ns_x) << ST_SHIFT) + (t >> 3);
 		if (x < grid_x && y < grid_y)
-			tile_count[y * grid_x + x] = total;
+			st_relaxed(tile_count + y * grid_x + x, total);
 	}
-}
-
-// Exclusive scan of the per-tile counts in tile-id order -> tile_start, and the tile ranges
-// (reference identifyTileRanges: tiles without instances keep (0, 0)).  One CTA.
-__global__ void __launch_bounds__(1024)
-    tile_offsets_kernel(const uint32_t* __restrict__ tile_count, uint32_t num_tiles, uint32_t* __restrict__ tile_start,
-                        uint2* __restrict__ ranges)
-{
-	__shared__ uint32_t s_warp[32];
-	__shared__ uint32_t s_carry;
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x == 0)
-		s_carry = 0;
+	__threadfence();
 	__syncthreads();
-	for (uint32_t t0 = 0; t0 < num_tiles; t0 += 1024) {
-		const uint32_t t = t0 + threadIdx.x;
-		const uint32_t v = (t < num_tiles) ? tile_count[t] : 0u;
-		uint32_t incl = v;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= (uint32_t)o)
-				incl += n;
-		}
-		if (lane == 31)
-			s_warp[warp] = incl;
-		__syncthreads();
-		if (warp == 0) {
-			uint32_t w = s_warp[lane], wi = w;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
-				if (lane >= (uint32_t)o)
-					wi += n;
-			}
-			s_warp[lane] = wi - w; // exclusive over warps
-		}
-		__syncthreads();
-		const uint32_t start = s_carry + s_warp[warp] + incl - v;
-		if (t < num_tiles) {
-			tile_start[t] = start;
-			ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
-		}
-		__syncthreads();
-		if (threadIdx.x == 1023)
-			s_carry = start + v;
-		__syncthreads();
+	if (threadIdx.x == 0)
+		s_last = atomicAdd(done, 1u);
+	__syncthreads();
+	if (s_last != gridDim.x - 1)
+		return;
+	__threadfence();
+	// exclusive scan over all tiles in tile-id order: every thread takes a contiguous run of tiles
+	const uint32_t num_tiles = grid_x * grid_y;
+	const uint32_t chunk = (num_tiles + 255) / 256;
+	const uint32_t t0 = min(threadIdx.x * chunk, num_tiles), t1 = min(t0 + chunk, num_tiles);
+	uint32_t local = 0;
+	for (uint32_t i = t0; i < t1; i++)
+		local += ld_relaxed(tile_count + i);
+	uint32_t grand;
+	uint32_t start = block_exclusive_scan_256(local, s_warp, grand);
+	for (uint32_t i = t0; i < t1; i++) {
+		const uint32_t v = ld_relaxed(tile_count + i);
+		tile_start[i] = start;
+		ranges[i] = v ? make_uint2(min(start, R_cap), min(start + v, R_cap)) : make_uint2(0u, 0u);
+		start += v;
 	}
 }
 
-struct FineScratch {
-	uint2* coarse_ranges;  // [ns]
-	uint32_t* slice_base;  // [ns + 1]
-	uint32_t* tile_count;  // [num_tiles]
-	uint32_t* tile_start;  // [num_tiles]
-	uint32_t* table;       // [max_slices][64]
-	size_t total_bytes;
-};
-
-FineScratch carve_fine_scratch(void* scratch, size_t R1, uint32_t grid_x, uint32_t grid_y)
+template <class T>
+T* carve(char*& p, size_t count)
 {
-	FineScratch f{};
-	const size_t ns = (size_t)supertiles(grid_x) * supertiles(grid_y);
-	const size_t num_tiles = (size_t)grid_x * grid_y;
-	const size_t max_slices = R1 / FINE_SLICE + ns;
-	char* p = static_cast<char*>(scratch);
-	size_t off = 0;
-	f.coarse_ranges = reinterpret_cast<uint2*>(p + off);
-	off += align_up(sizeof(uint2) * ns, 256);
-	f.slice_base = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * (ns + 1), 256);
-	f.tile_count = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * num_tiles, 256);
-	f.tile_start = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * num_tiles, 256);
-	f.table = reinterpret_cast<uint32_t*>(p + off);
-	off += align_up(sizeof(uint32_t) * ST_TILES * (max_slices ? max_slices : 1), 256);
-	f.total_bytes = off;
-	return f;
+	T* r = reinterpret_cast<T*>(p);
+	p += align_up(sizeof(T) * (count ? count : 1), 256);
+	return r;
 }
 
 } // namespace
 
-size_t fine_scratch_bytes(size_t R1, uint32_t grid_x, uint32_t grid_y)
+// ---- host side --------------------------------------------------------------------------------------
+
+namespace {
+// Both carvers walk the zeroed and the plain area with the same code that sizes them (nullptr base).
+struct DepthCarve {
+	DepthScratch s;
+	size_t zero_bytes, plain_bytes;
+};
+DepthCarve carve_depth(void* zeroed, void* plain, size_t P, int passes)
 {
-	return carve_fine_scratch(nullptr, R1, grid_x, grid_y).total_bytes;
+	DepthCarve c{};
+	const size_t tiles = sort_tiles(P);
+	char* z = static_cast<char*>(zeroed);
+	c.s.ctl = carve<uint32_t>(z, DCTL_WORDS);
+	c.s.hist = carve<uint32_t>(z, 4 * RADIX);
+	c.s.status = carve<uint32_t>(z, (size_t)passes * tiles * RADIX);
+	c.zero_bytes = (size_t)(z - static_cast<char*>(zeroed));
+	char* p = static_cast<char*>(plain);
+	for (int i = 0; i < 2; i++) {
+		c.s.keys[i] = carve<uint32_t>(p, P);
+		c.s.vals[i] = carve<uint32_t>(p, P);
+	}
+	c.plain_bytes = (size_t)(p - static_cast<char*>(plain));
+	c.s.tiles = (uint32_t)tiles;
+	return c;
+}
+struct InstCarve {
+	InstScratch s;
+	size_t zero_bytes, plain_bytes;
+};
+InstCarve carve_inst(void* zeroed, void* plain, size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y)
+{
+	InstCarve c{};
+	const size_t ns = (size_t)supertiles(grid_x) * supertiles(grid_y);
+	const size_t num_tiles = (size_t)grid_x * grid_y;
+	const size_t tiles_r = sort_tiles(R1_cap);
+	const size_t emit_blocks = (P + EMIT_TILE - 1) / EMIT_TILE;
+	const size_t max_slices = R1_cap / FINE_SLICE + ns;
+	const int coarse_passes = ns > RADIX ? 2 : 1;
+	char* z = static_cast<char*>(zeroed);
+	c.s.ctl = carve<uint32_t>(z, ICTL_WORDS);
+	c.s.cell_count = carve<uint32_t>(z, ns);
+	c.s.emit_status = carve<uint32_t>(z, emit_blocks);
+	c.s.coarse_status = carve<uint32_t>(z, (size_t)coarse_passes * tiles_r * RADIX);
+	c.zero_bytes = (size_t)(z - static_cast<char*>(zeroed));
+	char* p = static_cast<char*>(plain);
+	c.s.cell_keys = carve<uint32_t>(p, R1_cap);
+	c.s.cell_ids = carve<uint32_t>(p, R1_cap);
+	c.s.tmp_keys = carve<uint32_t>(p, coarse_passes > 1 ? R1_cap : 0);
+	c.s.tmp_ids = carve<uint32_t>(p, coarse_passes > 1 ? R1_cap : 0);
+	c.s.coarse_list = carve<uint32_t>(p, R1_cap);
+	c.s.coarse_ranges = carve<uint2>(p, ns);
+	c.s.slice_base = carve<uint32_t>(p, ns + 1);
+	c.s.tile_count = carve<uint32_t>(p, num_tiles);
+	c.s.tile_start = carve<uint32_t>(p, num_tiles);
+	c.s.table = carve<uint32_t>(p, ST_TILES * max_slices);
+	c.plain_bytes = (size_t)(p - static_cast<char*>(plain));
+	c.s.coarse_tiles = (uint32_t)tiles_r;
+	c.s.coarse_passes = coarse_passes;
+	return c;
+}
+} // namespace
+
+size_t depth_zero_bytes(size_t P, int passes) { return carve_depth(nullptr, nullptr, P, passes).zero_bytes; }
+size_t depth_plain_bytes(size_t P) { return carve_depth(nullptr, nullptr, P, 1).plain_bytes; }
+DepthScratch carve_depth_scratch(void* zeroed, void* plain, size_t P, int passes) { return carve_depth(zeroed, plain, P, passes).s; }
+size_t inst_zero_bytes(size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y)
+{
+	return carve_inst(nullptr, nullptr, P, R1_cap, grid_x, grid_y).zero_bytes;
+}
+size_t inst_plain_bytes(size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y)
+{
+	return carve_inst(nullptr, nullptr, P, R1_cap, grid_x, grid_y).plain_bytes;
+}
+InstScratch carve_inst_scratch(void* zeroed, void* plain, size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y)
+{
+	return carve_inst(zeroed, plain, P, R1_cap, grid_x, grid_y).s;
 }
 
-cudaError_t launch_fine_binning(const uint32_t* sorted_coarse_keys, const uint32_t* coarse_list, size_t R1,
-                                const uint2* rect, uint32_t grid_x, uint32_t grid_y, uint32_t* point_list,
-                                uint2* ranges, void* scratch, cudaStream_t stream)
+namespace {
+PassArgs depth_pass_args(const BinPlan& pl, int p)
 {
-	const uint32_t ns_x = supertiles(grid_x), ns = ns_x * supertiles(grid_y);
-	const uint32_t num_tiles = grid_x * grid_y;
-	if (num_tiles == 0)
+	const DepthScratch& d = pl.d;
+	PassArgs a{};
+	const bool last = p == pl.depth_passes - 1;
+	a.kin = p == 0 ? pl.depth_key : d.keys[(p - 1) & 1];
+	a.vin = p == 0 ? nullptr : d.vals[(p - 1) & 1];
+	a.kout = last ? nullptr : d.keys[p & 1];
+	a.vout = last ? pl.order : d.vals[p & 1];
+	a.n = pl.P;
+	a.n_ptr = p == 0 ? nullptr : pl.hdr + HDR_V; // the first pass drops the culled Gaussians
+	a.hdr = pl.hdr;
+	a.shift = 8 * p;
+	a.bits = 8;
+	a.drop = p == 0;
+	a.hist = d.hist + p * RADIX;
+	a.fold_n = 0;
+	a.status = d.status + (size_t)p * d.tiles * RADIX;
+	a.ticket = d.ctl + DCTL_TICKET + p;
+	return a;
+}
+} // namespace
+
+// Depth sort of the visible Gaussians: (depth_key - bias, id) on `depth_passes` 8-bit digits -> `order`.
+// begin: histogram of the digits of `planned_passes` passes (+ the overflow word of the header) and the
+// first pass, none of which needs the host to know anything; rest: passes 1 .. depth_passes - 1.
+// With depth_passes == 1 the first pass already writes `order`, so depth_passes must be final by then
+// (pl.depth_passes == 1 is only planned from a previous call's key range; the exact path plans >= 2).
+cudaError_t launch_depth_sort_begin(const BinPlan& pl, int planned_passes, cudaStream_t stream)
+{
+	if (pl.P == 0)
 		return cudaSuccess;
-	FineScratch f = carve_fine_scratch(scratch, R1, grid_x, grid_y);
-	// coarse_ranges and tile_count start at zero (supertiles / tiles nothing touches are never written)
-	cudaError_t e = cudaMemsetAsync(f.coarse_ranges, 0, (char*)f.tile_start - (char*)f.coarse_ranges, stream);
-	if (e != cudaSuccess)
-		return e;
-	if (R1 > 0) {
-		tile_ranges_kernel<<<(uint32_t)((R1 + 255) / 256), 256, 0, stream>>>(sorted_coarse_keys, (uint32_t)R1,
-		                                                                      f.coarse_ranges);
-		count_launch();
+	HistArgs h{};
+	h.keys = pl.depth_key;
+	h.n = pl.P;
+	h.n_ptr = nullptr;
+	h.hdr = pl.hdr;
+	h.hdr_out = pl.hdr;
+	h.passes = planned_passes;
+	for (int p = 0; p < 4; p++) {
+		h.shift[p] = 8 * p;
+		h.bits[p] = 8;
 	}
-	fine_plan_kernel<<<1, SORT_THREADS, 0, stream>>>(f.coarse_ranges, ns, f.slice_base);
+	h.drop = 1;
+	h.R_cap = pl.R_cap;
+	h.R1_cap = pl.R1_cap;
+	h.hist = pl.d.hist;
+	const uint32_t hist_grid = (uint32_t)std::min<size_t>((pl.P + 2047) / 2048, 296);
+	radix_hist_kernel<<<hist_grid, OS_THREADS, 0, stream>>>(h);
 	count_launch();
-	const uint32_t max_slices = (uint32_t)(R1 / FINE_SLICE + ns);
-	const uint32_t blocks = (max_slices + FINE_WARPS - 1) / FINE_WARPS;
-	if (R1 > 0) {
-		fine_kernel<false><<<blocks, FINE_WARPS * 32, 0, stream>>>(coarse_list, f.coarse_ranges, f.slice_base, rect, ns,
-		                                                            ns_x, grid_x, grid_y, f.table, nullptr, nullptr);
-		count_launch();
-		fine_scan_kernel<<<ns, 256, 0, stream>>>(f.table, f.slice_base, ns_x, grid_x, grid_y, f.tile_count);
-		count_launch();
-	}
-	tile_offsets_kernel<<<1, 1024, 0, stream>>>(f.tile_count, num_tiles, f.tile_start, ranges);
+	onesweep_kernel<<<pl.d.tiles, OS_THREADS, 0, stream>>>(depth_pass_args(pl, 0));
 	count_launch();
-	if (R1 > 0) {
-		fine_kernel<true><<<blocks, FINE_WARPS * 32, 0, stream>>>(coarse_list, f.coarse_ranges, f.slice_base, rect, ns,
-		                                                           ns_x, grid_x, grid_y, f.table, f.tile_start, point_list);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_depth_sort_rest(const BinPlan& pl, cudaStream_t stream)
+{
+	if (pl.P == 0)
+		return cudaSuccess;
+	for (int p = 1; p < pl.depth_passes; p++) {
+		onesweep_kernel<<<pl.d.tiles, OS_THREADS, 0, stream>>>(depth_pass_args(pl, p));
 		count_launch();
 	}
 	return cudaGetLastError();
 }
 
-cudaError_t launch_tile_ranges(const uint32_t* sorted_tile_keys, size_t R, uint2* ranges, cudaStream_t stream)
+cudaError_t launch_emit(const BinPlan& pl, cudaStream_t stream)
 {
-	if (R == 0)
+	const InstScratch& b = pl.i;
+	if (pl.P == 0)
 		return cudaSuccess;
-	tile_ranges_kernel<<<(uint32_t)((R + 255) / 256), 256, 0, stream>>>(sorted_tile_keys, (uint32_t)R, ranges);
+	EmitArgs a{};
+	a.order = pl.order;
+	a.rect = pl.rect;
+	a.hdr = pl.hdr;
+	a.shift = ST_SHIFT;
+	a.ns_x = pl.ns_x;
+	a.ns = pl.ns;
+	a.cell_keys = b.cell_keys;
+	a.cell_ids = b.cell_ids;
+	a.R1_cap = pl.R1_cap;
+	a.status = b.emit_status;
+	a.ticket = b.ctl + ICTL_EMIT_TICKET;
+	a.done = b.ctl + ICTL_EMIT_DONE;
+	a.cell_count = b.cell_count;
+	a.coarse_ranges = b.coarse_ranges;
+	a.slice_base = b.slice_base;
+	a.n_instances = b.ctl + ICTL_N_INSTANCES;
+	const uint32_t blocks = (uint32_t)((pl.P + EMIT_TILE - 1) / EMIT_TILE);
+	emit_kernel<<<blocks, EMIT_THREADS, 0, stream>>>(a);
 	count_launch();
+	return cudaGetLastError();
+}
+
+// Stable radix pass(es) on the supertile id: (cell_keys, cell_ids) -> coarse_list.
+cudaError_t launch_coarse_sort(const BinPlan& pl, cudaStream_t stream)
+{
+	const InstScratch& b = pl.i;
+	if (pl.P == 0 || pl.R1_cap == 0)
+		return cudaSuccess;
+	int nbits = 1;
+	while ((1u << nbits) < pl.ns)
+		nbits++;
+	const int passes = b.coarse_passes;
+	const int lo_bits = passes == 1 ? nbits : nbits / 2;
+	if (nbits - lo_bits > 8 || lo_bits > 8)
+		return cudaErrorInvalidValue; // more than 65536 supertiles (image beyond 32768 x 32768 px)
+	for (int p = 0; p < passes; p++) {
+		PassArgs a{};
+		const bool last = p == passes - 1;
+		a.kin = p == 0 ? b.cell_keys : b.tmp_keys;
+		a.vin = p == 0 ? b.cell_ids : b.tmp_ids;
+		a.kout = last ? nullptr : b.tmp_keys;
+		a.vout = last ? b.coarse_list : b.tmp_ids;
+		a.n = pl.R1_cap;
+		a.n_ptr = b.ctl + ICTL_N_INSTANCES;
+		a.hdr = nullptr;
+		a.shift = p == 0 ? 0 : lo_bits;
+		a.bits = p == 0 ? lo_bits : nbits - lo_bits;
+		a.drop = 0;
+		a.hist = b.cell_count;
+		a.fold_n = pl.ns;
+		a.status = b.coarse_status + (size_t)p * b.coarse_tiles * RADIX;
+		a.ticket = b.ctl + ICTL_COARSE_TICKET + p;
+		onesweep_kernel<<<b.coarse_tiles, OS_THREADS, 0, stream>>>(a);
+		count_launch();
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_fine_binning(const BinPlan& pl, cudaStream_t stream)
+{
+	const InstScratch& b = pl.i;
+	const uint32_t num_tiles = pl.grid_x * pl.grid_y;
+	if (num_tiles == 0 || pl.P == 0)
+		return cudaSuccess;
+	const uint32_t max_slices = (uint32_t)(pl.R1_cap / FINE_SLICE + pl.ns);
+	const uint32_t blocks = (max_slices + FINE_WARPS - 1) / FINE_WARPS;
+	if (pl.R1_cap > 0) {
+		fine_kernel<false><<<blocks, FINE_WARPS * 32, 0, stream>>>(b.coarse_list, b.coarse_ranges, b.slice_base, pl.rect, pl.ns,
+		                                                            pl.ns_x, pl.grid_x, pl.grid_y, b.table, nullptr, nullptr, 0u);
+		count_launch();
+	}
+	fine_scan_kernel<<<pl.ns, 256, 0, stream>>>(b.table, b.slice_base, pl.ns_x, pl.grid_x, pl.grid_y, b.tile_count,
+	                                            b.tile_start, pl.ranges, pl.R_cap, b.ctl + ICTL_FINE_DONE);
+	count_launch();
+	if (pl.R1_cap > 0 && pl.R_cap > 0) {
+		fine_kernel<true><<<blocks, FINE_WARPS * 32, 0, stream>>>(b.coarse_list, b.coarse_ranges, b.slice_base, pl.rect, pl.ns,
+		                                                           pl.ns_x, pl.grid_x, pl.grid_y, b.table, b.tile_start,
+		                                                           pl.point_list, pl.R_cap);
+		count_launch();
+	}
+	return cudaGetLastError();
+}
+
+// ---- stand-alone stable sort of (u32, u32) pairs (C-ABI brs_sort_pairs_u32, tests, tools/sort_vs_cub) ----
+
+namespace {
+struct PairSortScratch {
+	uint32_t* ctl;    // [64] tickets
+	uint32_t* hist;   // [4][RADIX]
+	uint32_t* status; // [4][tiles][RADIX]
+	size_t zero_bytes;
+	uint32_t* tmp_keys;
+	uint32_t* tmp_vals;
+	size_t total_bytes;
+};
+PairSortScratch carve_pair_sort(void* scratch, size_t n)
+{
+	PairSortScratch s{};
+	char* p = static_cast<char*>(scratch);
+	s.ctl = carve<uint32_t>(p, 64);
+	s.hist = carve<uint32_t>(p, 4 * RADIX);
+	s.status = carve<uint32_t>(p, 4 * (size_t)sort_tiles(n) * RADIX);
+	s.zero_bytes = (size_t)(p - static_cast<char*>(scratch));
+	s.tmp_keys = carve<uint32_t>(p, n);
+	s.tmp_vals = carve<uint32_t>(p, n);
+	s.total_bytes = (size_t)(p - static_cast<char*>(scratch));
+	return s;
+}
+} // namespace
+
+size_t sort_scratch_bytes(size_t n) { return carve_pair_sort(nullptr, n).total_bytes; }
+
+cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                       size_t n, int begin_bit, int end_bit, void* scratch, cudaStream_t stream)
+{
+	if (n == 0)
+		return cudaSuccess;
+	int nbits = end_bit - begin_bit;
+	if (nbits < 1)
+		nbits = 1;
+	const int passes = (nbits + 7) / 8;
+	const int base_bits = nbits / passes, extra = nbits % passes;
+	PairSortScratch s = carve_pair_sort(scratch, n);
+	cudaError_t e = cudaMemsetAsync(scratch, 0, s.zero_bytes, stream);
+	if (e != cudaSuccess)
+		return e;
+	HistArgs h{};
+	h.keys = keys_in;
+	h.n = (uint32_t)n;
+	h.passes = passes;
+	int shift = begin_bit;
+	for (int p = 0; p < passes; p++) {
+		h.shift[p] = shift;
+		h.bits[p] = base_bits + (p < extra ? 1 : 0);
+		shift += h.bits[p];
+	}
+	h.hist = s.hist;
+	const uint32_t tiles = sort_tiles(n);
+	radix_hist_kernel<<<(uint32_t)std::min<size_t>((n + 2047) / 2048, 296), OS_THREADS, 0, stream>>>(h);
+	count_launch();
+	const uint32_t* kin = keys_in;
+	const uint32_t* vin = vals_in;
+	for (int p = 0; p < passes; p++) {
+		const bool to_out = ((passes - 1 - p) & 1) == 0;
+		PassArgs a{};
+		a.kin = kin;
+		a.vin = vin;
+		a.kout = to_out ? keys_out : s.tmp_keys;
+		a.vout = to_out ? vals_out : s.tmp_vals;
+		a.n = (uint32_t)n;
+		a.shift = h.shift[p];
+		a.bits = h.bits[p];
+		a.hist = s.hist + p * RADIX;
+		a.status = s.status + (size_t)p * tiles * RADIX;
+		a.ticket = s.ctl + p;
+		onesweep_kernel<<<tiles, OS_THREADS, 0, stream>>>(a);
+		count_launch();
+		kin = a.kout;
+		vin = a.vout;
+	}
 	return cudaGetLastError();
 }
 

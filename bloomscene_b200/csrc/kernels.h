@@ -57,38 +57,85 @@ cudaError_t launch_check_frustum(int P, const float* means3D, const float* viewm
                                  cudaStream_t stream);
 
 // ---- binning.cu ---------------------------------------------------------------------------------
-// Stable LSD radix sort of (u32,u32) pairs, onesweep-style (single pass per digit with decoupled
-// look-back).  Scratch layout is private; size from sort_scratch_bytes(n).
+// Words of the geometry header (device memory, zeroed before preprocess).  preprocess accumulates
+// 0..4; the depth sort's histogram kernel writes 5..6.
+enum HeaderWord : int {
+	HDR_R = 0,          // tile instances (reference num_rendered)
+	HDR_R1 = 1,         // supertile instances
+	HDR_KEY_INVMIN = 2, // max over visible Gaussians of ~depth bits (= ~min)
+	HDR_KEY_MAX = 3,    // max depth bits over visible Gaussians
+	HDR_V = 4,          // visible Gaussians
+	HDR_OVERFLOW = 5,   // bit 0: R > R_cap, bit 1: R1 > R1_cap, bit 2: depth keys need more bits than planned
+	HDR_KEY_BITS = 6,   // significant bits of (max key - bias)
+	HDR_WORDS = 8
+};
+enum DepthCtl : int { DCTL_TICKET = 0 /* one per pass */, DCTL_WORDS = 16 };
+enum InstCtl : int { ICTL_EMIT_TICKET = 0, ICTL_EMIT_DONE = 1, ICTL_N_INSTANCES = 2, ICTL_FINE_DONE = 3, ICTL_COARSE_TICKET = 4 /* one per pass */, ICTL_WORDS = 16 };
+
+// Scratch of the depth sort: a zeroed part (tickets, digit histograms, look-back status words) and
+// a plain part (ping-pong pairs).
+struct DepthScratch {
+	uint32_t* ctl;    // [DCTL_WORDS]
+	uint32_t* hist;   // [4][256]
+	uint32_t* status; // [passes][tiles][256]
+	uint32_t* keys[2];
+	uint32_t* vals[2];
+	uint32_t tiles;
+};
+size_t depth_zero_bytes(size_t P, int passes);
+size_t depth_plain_bytes(size_t P);
+DepthScratch carve_depth_scratch(void* zeroed, void* plain, size_t P, int passes);
+
+// Scratch of the instance levels (emission, coarse sort, fine binning), sized by the CAPACITY R1_cap.
+struct InstScratch {
+	uint32_t* ctl;           // [ICTL_WORDS]
+	uint32_t* cell_count;    // [ns]
+	uint32_t* emit_status;   // [emit blocks]
+	uint32_t* coarse_status; // [coarse passes][tiles][256]
+	uint32_t* cell_keys;     // [R1_cap]
+	uint32_t* cell_ids;      // [R1_cap]
+	uint32_t* tmp_keys;      // [R1_cap] (two coarse passes only)
+	uint32_t* tmp_ids;
+	uint32_t* coarse_list;   // [R1_cap] ids in (supertile, depth, id) order
+	uint2* coarse_ranges;    // [ns]
+	uint32_t* slice_base;    // [ns + 1]
+	uint32_t* tile_count;    // [tiles]
+	uint32_t* tile_start;    // [tiles]
+	uint32_t* table;         // [max slices][64]
+	uint32_t coarse_tiles;
+	int coarse_passes;
+};
+size_t inst_zero_bytes(size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y);
+size_t inst_plain_bytes(size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y);
+InstScratch carve_inst_scratch(void* zeroed, void* plain, size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y);
+
+// One forward's binning: capacities from the host, counts from the header on the device.
+struct BinPlan {
+	uint32_t P, R1_cap, R_cap;
+	uint32_t grid_x, grid_y, ns_x, ns;
+	int depth_passes;          // 8-bit digits of (depth key - bias) that are sorted on
+	uint32_t* hdr;             // geometry header
+	const uint32_t* depth_key; // [P]
+	const uint2* rect;         // [P]
+	uint32_t* order;           // [P]: the V visible ids in (depth bits, id) order
+	uint32_t* point_list;      // [R_cap]
+	uint2* ranges;             // [tiles]
+	DepthScratch d;
+	InstScratch i;
+};
+// Histogram of all digits + first pass (needs no host knowledge), then the remaining passes.
+cudaError_t launch_depth_sort_begin(const BinPlan& pl, int planned_passes, cudaStream_t stream);
+cudaError_t launch_depth_sort_rest(const BinPlan& pl, cudaStream_t stream);
+cudaError_t launch_emit(const BinPlan& pl, cudaStream_t stream);
+cudaError_t launch_coarse_sort(const BinPlan& pl, cudaStream_t stream);
+cudaError_t launch_fine_binning(const BinPlan& pl, cudaStream_t stream);
+
+// Stand-alone stable LSD radix sort of (u32,u32) pairs on key bits [begin_bit, end_bit) with the same
+// kernels (one histogram kernel + one onesweep kernel per 8-bit digit).  vals_in == nullptr -> iota.
+// The result is written to keys_out/vals_out; the inputs are not modified.
 size_t sort_scratch_bytes(size_t n);
-// Sorts on key bits [begin_bit, end_bit).  vals_in == nullptr -> iota.  The result is written to
-// keys_out/vals_out; keys_in/vals_in are not modified.  tmp buffers for ping-pong live in scratch.
 cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                        size_t n, int begin_bit, int end_bit, void* scratch, cudaStream_t stream);
-// One stable pass on the digit ((key - bias) >> shift) & ((1 << bits) - 1), bits <= 8; in != out.
-// With `drop`, keys equal to `drop_key` are left out: the output then holds only the other keys
-// (compacted, still stable) and the caller continues with the smaller count.
-cudaError_t sort_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
-                      uint32_t bias, int shift, int bits, void* scratch, cudaStream_t stream, bool drop = false,
-                      uint32_t drop_key = 0);
-// The ping-pong buffers inside a sort scratch area (n keys + n values).
-void sort_tmp_buffers(void* scratch, size_t n, uint32_t** tmp_keys, uint32_t** tmp_vals);
-
-// Fused exclusive scan of per-Gaussian cell counts (in depth order) + emission of (cell, id)
-// instances, a cell being (1 << shift)^2 tiles and grid_x the number of cells per row.
-// `order` = Gaussian ids sorted by depth; `rect` packed tile rectangles.
-size_t emit_scratch_bytes(size_t P);
-cudaError_t launch_emit(const uint32_t* order, const uint2* rect, size_t P, uint32_t shift, uint32_t grid_x,
-                        uint32_t* cell_keys, uint32_t* inst_ids, size_t n_instances, void* scratch, cudaStream_t stream);
-
-// ranges[key] = [first, last+1) in a sorted key list; `ranges` must be pre-zeroed.
-cudaError_t launch_tile_ranges(const uint32_t* sorted_keys, size_t n, uint2* ranges, cudaStream_t stream);
-
-// Fine level of the binning: per-supertile lists (sorted_coarse_keys / coarse_list, R1 entries in
-// (supertile, depth, id) order) -> point_list (R ids in (tile, depth, id) order) and tile ranges.
-size_t fine_scratch_bytes(size_t R1, uint32_t grid_x, uint32_t grid_y);
-cudaError_t launch_fine_binning(const uint32_t* sorted_coarse_keys, const uint32_t* coarse_list, size_t R1,
-                                const uint2* rect, uint32_t grid_x, uint32_t grid_y, uint32_t* point_list,
-                                uint2* ranges, void* scratch, cudaStream_t stream);
 
 // ---- blend_fwd.cu -------------------------------------------------------------------------------
 struct BlendFwdArgs {

@@ -82,13 +82,18 @@ brs_stream current_stream() { return reinterpret_cast<brs_stream>(c10::cuda::get
 
 } // namespace
 
-std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
-RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
-                       const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
-                       const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
-                       const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
-                       const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
-                       const torch::Tensor& campos, const bool prefiltered, const bool debug)
+using ForwardTuple = std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
+
+// Extension of the reference binding: the same 19 arguments plus brs_fwd_options (include/bloomrast.h).
+// `report`: pinned CPU int32[8] that a DEFERRED forward fills asynchronously.
+ForwardTuple RasterizeGaussiansExCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                                      const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                      const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                                      const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+                                      const float tan_fovy, const int image_height, const int image_width,
+                                      const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+                                      const bool prefiltered, const bool debug, const int mode, const int R_cap,
+                                      const int R1_cap, const int depth_bits, const c10::optional<torch::Tensor>& report)
 {
 	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
 		AT_ERROR("means3D must have dimensions (num_points, 3)");
@@ -138,11 +143,36 @@ RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& mea
 	g.cov3D_precomp = opt_ptr(cov3D_precomp, k[10], "cov3D_precomp");
 	view.sh_coeffs = (g.shs != nullptr) ? (int)sh.size(1) : 0; // rasterize_points.cu:84-88
 
+	brs_fwd_options opt{};
+	opt.mode = mode;
+	opt.R_cap = R_cap;
+	opt.R1_cap = R1_cap;
+	opt.depth_bits = depth_bits;
+	if (report.has_value() && report->defined()) {
+		TORCH_CHECK(report->is_cpu() && report->is_pinned() && report->scalar_type() == torch::kInt32 && report->numel() >= 8 &&
+		                report->is_contiguous(),
+		            "report must be a pinned contiguous CPU int32 tensor of at least 8 elements");
+		opt.report = reinterpret_cast<uint32_t*>(report->data_ptr<int>());
+	}
 	brs_fwd_state state{};
-	int st = brs_forward(&view, &g, out_color.data_ptr<float>(), out_depth.data_ptr<float>(),
-	                     P ? radii.data_ptr<int>() : nullptr, alloc_cb, &ctx, &state, current_stream());
+	int st = brs_forward_ex(&view, &g, out_color.data_ptr<float>(), out_depth.data_ptr<float>(),
+	                        P ? radii.data_ptr<int>() : nullptr, alloc_cb, &ctx, &state, &opt, current_stream());
 	check_status(st, "rasterize_gaussians");
 	return std::make_tuple(state.num_rendered, out_color, out_depth, radii, ctx.geom, ctx.binning, ctx.image);
+}
+
+// reference binding (rasterize_points.h:18-40): 19 arguments
+ForwardTuple RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                                    const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                    const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                                    const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+                                    const float tan_fovy, const int image_height, const int image_width,
+                                    const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+                                    const bool prefiltered, const bool debug)
+{
+	return RasterizeGaussiansExCUDA(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+	                                viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+	                                prefiltered, debug, BRS_FWD_AUTO, 0, 0, 0, c10::nullopt);
 }
 
 namespace {
@@ -515,6 +545,25 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	// the forward blocks once on the device (instance count); it touches no Python object, so it runs
 	// without the GIL and several host threads can drive one CUDA stream each (render_views)
 	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
+	m.def("rasterize_gaussians_ex", &RasterizeGaussiansExCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
+	m.def("note_counts", [](int P, int W, int H, const torch::Tensor& report) {
+		TORCH_CHECK(report.is_cpu() && report.scalar_type() == torch::kInt32 && report.numel() >= 8 && report.is_contiguous());
+		brs_note_counts(P, W, H, reinterpret_cast<const uint32_t*>(report.data_ptr<int>()));
+	});
+	m.def("reset_marks", []() { brs_reset_marks(); });
+	m.def("forward_stats", [](bool reset) {
+		long long v[4];
+		brs_forward_stats(v, reset ? 1 : 0);
+		pybind11::dict d;
+		d["exact"] = v[0];
+		d["optimistic"] = v[1];
+		d["overflow_reruns"] = v[2];
+		d["deferred"] = v[3];
+		return d;
+	}, pybind11::arg("reset") = false);
+	m.attr("FWD_AUTO") = (int)BRS_FWD_AUTO;
+	m.attr("FWD_EXACT") = (int)BRS_FWD_EXACT;
+	m.attr("FWD_DEFERRED") = (int)BRS_FWD_DEFERRED;
 	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
 	m.def("rasterize_gaussians_backward_accumulate", &RasterizeGaussiansBackwardAccumulateCUDA,
 	      pybind11::call_guard<pybind11::gil_scoped_release>());

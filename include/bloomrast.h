@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BRS_VERSION 101 /* 0.1.1: brs_grads gained depth_gradient / out_depth */
+#define BRS_VERSION 200 /* 0.2.0: optimistic and deferred forward, see brs_forward_ex */
 
 typedef struct CUstream_st* brs_stream; /* == cudaStream_t */
 
@@ -95,7 +95,7 @@ typedef struct brs_fwd_state {
 	size_t binning_bytes;
 	void* image;
 	size_t image_bytes;
-	int num_rendered; /* R = number of (tile, Gaussian) instances */
+	int num_rendered; /* R = number of (tile, Gaussian) instances; -1 after a DEFERRED forward (it stayed on the device) */
 } brs_fwd_state;
 
 /* Gradient outputs (reference rasterize_points.cu:154-162).  Every pointer that is non-NULL is
@@ -133,12 +133,49 @@ typedef struct brs_grads {
 /* Replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:32-57, rasterizer_impl.cu:198-339).
  * Writes out_color [3,H,W] (planar), out_depth [1,H,W], radii [P]; all three are fully written.
  * P == 0 writes zeros and returns R = 0 (reference skips the kernels: rasterize_points.cu:82).
- * Performs ONE host wait (for R, to size the binning buffer) like the reference
- * (rasterizer_impl.cu:282) — but overlapped with the depth sort. */
+ * Performs at most ONE host wait (for R) like the reference (rasterizer_impl.cu:282); see
+ * brs_fwd_options for when it happens.  Same as brs_forward_ex with opt == NULL. */
 int brs_forward(const brs_view* view, const brs_gaussians* g,
                 float* out_color, float* out_depth, int* radii,
                 brs_alloc_fn alloc, void* alloc_ctx,
                 brs_fwd_state* state, brs_stream stream);
+
+/* Extension: how the forward learns its instance counts.  The reference copies num_rendered to the host
+ * with a blocking cudaMemcpy between its scan and its sort (rasterizer_impl.cu:282) and sizes the
+ * binning buffer from it.  Here every kernel after preprocess reads the counts from the device and takes
+ * only CAPACITIES from the host, so the host does not have to know them before it launches:
+ *   BRS_FWD_AUTO     (default) the first forward of a (device, P, W, H) shape runs EXACT; later ones size
+ *                    their buffers from the high-water marks of that shape (+25 %), enqueue everything
+ *                    through the blend, and only then wait for the header that left the device right
+ *                    after preprocess — the GPU never drains.  If a capacity was too small (the header's
+ *                    overflow word) the binning and the blend are run again with the exact sizes.
+ *   BRS_FWD_EXACT    wait for the counts right after preprocess, then size exactly (reference behaviour).
+ *   BRS_FWD_DEFERRED no host wait at all: capacities from this struct (0 = the high-water marks); the
+ *                    8-word header {R, R1, ~min depth key, max depth key, V, overflow, key bits, 0} is copied
+ *                    asynchronously to `report` (pinned host memory).  state->num_rendered is -1.  The caller
+ *                    inspects report[5] after it has synchronised with the stream for its own reasons — e.g.
+ *                    once per batch of views — and repeats the overflowed forwards in EXACT mode.  A deferred
+ *                    forward (and the backward of its state) can be captured in a CUDA graph.
+ * Results are bit-identical in all three modes. */
+enum { BRS_FWD_AUTO = 0, BRS_FWD_EXACT = 1, BRS_FWD_DEFERRED = 2 };
+typedef struct brs_fwd_options {
+	int mode;
+	int R_cap;        /* DEFERRED: capacity of the binning buffer in tile instances (0: high-water mark) */
+	int R1_cap;       /* DEFERRED: capacity in supertile instances (0: high-water mark) */
+	int depth_bits;   /* DEFERRED: significant depth-key bits to sort on (0: high-water mark) */
+	uint32_t* report; /* DEFERRED: 8 words of pinned host memory */
+} brs_fwd_options;
+int brs_forward_ex(const brs_view* view, const brs_gaussians* g,
+                   float* out_color, float* out_depth, int* radii,
+                   brs_alloc_fn alloc, void* alloc_ctx,
+                   brs_fwd_state* state, const brs_fwd_options* opt, brs_stream stream);
+/* Feeds the counts of a DEFERRED forward's report back into the high-water marks of its shape. */
+void brs_note_counts(int P, int image_width, int image_height, const uint32_t* report);
+/* Per calling thread: out[0] = EXACT forwards, out[1] = optimistic ones, out[2] = of those, re-run because a
+ * capacity overflowed, out[3] = DEFERRED ones. */
+void brs_forward_stats(long long* out, int reset);
+/* Forgets all high-water marks (the next forward of every shape runs EXACT again). */
+void brs_reset_marks(void);
 
 /* Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:78-105, rasterizer_impl.cu:403-504).
  * dL_dout_depth is accepted and, unless grads->depth_gradient is set, ignored: the reference plumbs it

@@ -457,3 +457,80 @@ def test_fuzz_small_scenes_vs_reference_cuda():
             _assert_grad_parity(pl.compare_autograd(scene, cam, bg, Wc, Wd, scale_modifier=mod))
         except AssertionError as e:
             raise AssertionError(f"fuzz case {tag}: {e}") from e
+
+
+def _fwd_ex(_C, scene, cam, bg, mode, mod=1.0, R_cap=0, R1_cap=0, depth_bits=0, report=None):
+    return _C.rasterize_gaussians_ex(*pl.forward_args(scene, cam, bg, scale_modifier=mod), mode, R_cap, R1_cap, depth_bits, report)
+
+
+def _same_forward(_C, a, b, P, W, H):
+    from bloomscene_b200.debug import state_views
+
+    Ra, Rb = a[0], b[0]
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    R = max(Ra, Rb)
+    sa, sb = state_views(_C, a[4], a[5], a[6], P, R, W, H), state_views(_C, b[4], b[5], b[6], P, R, W, H)
+    for k in ("point_list", "ranges", "n_contrib", "final_T", "depth_key", "rect"):
+        assert torch.equal(sa[k], sb[k]), k
+
+
+def test_forward_modes_are_bit_identical_and_an_overflow_reruns():
+    """brs_fwd_options: EXACT (host waits for the counts after preprocess), AUTO (capacities from the high-water
+    marks, host waits only after everything is enqueued) and DEFERRED (no host wait) must give identical bits;
+    a forward whose capacities were too small must be detected and re-run with the exact sizes."""
+    _C = pl.ours()._C
+    scene = synthetic.make_scene(20_000, "object", "sh1", -4.2, seed=3).to(DEV)
+    cam = synthetic.orbit_camera(272, 208, 0.7).to(DEV)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    P, W, H = scene.P, 272, 208
+    _C.reset_marks()
+    _C.forward_stats(True)
+    exact = _fwd_ex(_C, scene, cam, bg, _C.FWD_EXACT)
+    first = _fwd_ex(_C, scene, cam, bg, _C.FWD_AUTO)   # marks exist already (EXACT raised them): optimistic
+    second = _fwd_ex(_C, scene, cam, bg, _C.FWD_AUTO)
+    st = _C.forward_stats(False)
+    assert st["exact"] == 1 and st["optimistic"] == 2 and st["overflow_reruns"] == 0, st
+    assert exact[0] == first[0] == second[0] > 1000
+    _same_forward(_C, exact, first, P, W, H)
+    _same_forward(_C, exact, second, P, W, H)
+    # same shape, 3x larger Gaussians: ~9x the instances -> the marks' capacity overflows -> re-run
+    big_auto = _fwd_ex(_C, scene, cam, bg, _C.FWD_AUTO, mod=3.0)
+    st = _C.forward_stats(False)
+    assert st["overflow_reruns"] == 1, st
+    big_exact = _fwd_ex(_C, scene, cam, bg, _C.FWD_EXACT, mod=3.0)
+    assert big_auto[0] == big_exact[0] > 3 * exact[0]
+    _same_forward(_C, big_exact, big_auto, P, W, H)
+    # the marks were raised: the next optimistic forward fits
+    again = _fwd_ex(_C, scene, cam, bg, _C.FWD_AUTO, mod=3.0)
+    assert _C.forward_stats(False)["overflow_reruns"] == 1
+    _same_forward(_C, big_exact, again, P, W, H)
+    # a view with a much wider depth range than the marks have seen (more key bits): re-run as well
+    far = synthetic.Scene(scene.means3D.clone(), scene.scales, scene.rotations, scene.opacities, scene.shs, None, scene.sh_degree)
+    far.means3D[::7, 2] += 400.0
+    far_auto = _fwd_ex(_C, far, cam, bg, _C.FWD_AUTO)
+    far_exact = _fwd_ex(_C, far, cam, bg, _C.FWD_EXACT)
+    _same_forward(_C, far_exact, far_auto, P, W, H)
+
+    # DEFERRED: no host wait; counts arrive in the pinned report
+    report = torch.zeros(8, dtype=torch.int32).pin_memory()
+    dfr = _fwd_ex(_C, scene, cam, bg, _C.FWD_DEFERRED, report=report)
+    torch.cuda.synchronize()
+    assert dfr[0] == -1 and int(report[0]) == exact[0] and int(report[5]) == 0 and int(report[4]) == int((exact[3] > 0).sum())
+    _same_forward(_C, exact, (exact[0],) + tuple(dfr[1:]), P, W, H)
+    # backward of a deferred state (num_rendered = -1) equals the backward of the exact one
+    Wc, _ = (t.to(DEV) for t in synthetic.loss_weights(W, H))
+    e = torch.Tensor([])
+
+    def bwd(fw):
+        return _C.rasterize_gaussians_backward(bg, scene.means3D, fw[3], e, scene.scales, scene.rotations, 1.0, e,
+                                               cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, Wc, e, scene.shs,
+                                               scene.sh_degree, cam.campos, fw[4], fw[0], fw[5], fw[6], False)
+
+    for ga, gb in zip(bwd(exact), bwd(dfr)):
+        assert pl.rel_l2(ga, gb) <= 1e-5
+    # DEFERRED with capacities that are far too small: flagged, memory-safe, nothing hangs
+    tiny = _fwd_ex(_C, scene, cam, bg, _C.FWD_DEFERRED, R_cap=64, R1_cap=32, depth_bits=8, report=report)
+    torch.cuda.synchronize()
+    assert int(report[5]) & 3 == 3 and int(report[0]) == exact[0]
+    assert torch.isfinite(tiny[1]).all()
+    _C.reset_marks()

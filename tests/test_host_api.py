@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_sizes_and_error_strings():
     lib = _lib()
-    assert lib.brs_version() == 101
+    assert lib.brs_version() == 200
     for f in ("brs_geom_bytes", "brs_binning_bytes", "brs_sort_scratch_bytes", "brs_backward_scratch_bytes"):
         getattr(lib, f).restype = C.c_size_t
     lib.brs_image_bytes.restype = C.c_size_t

@@ -217,12 +217,21 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(PassArgs a)
 	const uint32_t valid_count = min((uint32_t)OS_TILE, n - base);
 
 	// load keys (warp-striped: coalesced, and rank order == index order)
-	uint32_t key[OS_ITEMS], rank[OS_ITEMS];
+	// (values are fetched here as well, unconditionally: fetched where they are stored, behind the `valid`
+	// branch, the OS_ITEMS loads would be issued one after the other, each exposing its full latency)
+	uint32_t key[OS_ITEMS], val[OS_ITEMS], rank[OS_ITEMS];
 	const uint32_t wbase = warp * (32 * OS_ITEMS) + lane;
 #pragma unroll
 	for (int i = 0; i < OS_ITEMS; i++) {
 		const uint32_t li = wbase + i * 32;
 		key[i] = (li < valid_count) ? __ldg(a.kin + base + li) : 0xffffffffu;
+	}
+#pragma unroll
+	for (int i = 0; i < OS_ITEMS; i++) {
+		const uint32_t li = wbase + i * 32;
+		val[i] = base + li;
+		if (a.vin != nullptr && li < valid_count)
+			val[i] = __ldg(a.vin + base + li);
 	}
 	// digit totals over the whole input (independent of the ranking below)
 	uint32_t digit_total = 0;
@@ -276,8 +285,7 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(PassArgs a)
 		s_digit_start[tid] = digit_start;
 	__syncthreads();
 
-	// scatter into shared memory in sorted-by-digit order (values are fetched only now); this also
-	// gives the predecessors time to publish
+	// scatter into shared memory in sorted-by-digit order; this also gives the predecessors time to publish
 #pragma unroll
 	for (int i = 0; i < OS_ITEMS; i++) {
 		const uint32_t li = wbase + i * 32;
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(PassArgs a)
 			const uint32_t d = ((key[i] - bias) >> a.shift) & mask;
 			const uint32_t pos = s_digit_start[d] + s_cnt[warp][d] + rank[i];
 			s_keys[pos] = key[i];
-			s_vals[pos] = a.vin ? __ldg(a.vin + base + li) : base + li;
+			s_vals[pos] = val[i];
 		}
 	}
 
@@ -523,12 +531,27 @@ __device__ __forceinline__ uint32_t spread4(uint32_t b) // bit i of b (i < 4) ->
 	return (b * 0x00204081u) & 0x01010101u;
 }
 
+// In-warp transpose of a 32 x 32 bit matrix: lane i holds row i (bit j = element (i, j)); afterwards lane i
+// holds column i (bit j = element (j, i)).  Five butterfly stages, each swapping the off-diagonal k x k blocks.
+__device__ __forceinline__ uint32_t transpose32(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+	for (int s = 0; s < 5; s++) {
+		const uint32_t k = 16u >> s;
+		const uint32_t m = s == 0 ? 0x0000FFFFu : (s == 1 ? 0x00FF00FFu : (s == 2 ? 0x0F0F0F0Fu : (s == 3 ? 0x33333333u : 0x55555555u)));
+		const uint32_t x = __shfl_xor_sync(0xffffffffu, v, k);
+		v = (lane & k) ? ((v & ~m) | ((x >> k) & m)) : ((v & m) | ((x << k) & ~m));
+	}
+	return v;
+}
+
 // One warp per slice of <= FINE_SLICE consecutive entries of one supertile's list.  Entries are read 32
 // at a time (lane = entry, list order): each lane builds the 64-bit mask of the supertile's tiles its
-// rectangle covers.  Then the roles flip: lane t OWNS local tiles t (rows 0..3) and t + 32 (rows 4..7)
-// and the warp walks the 32 entries in list order, broadcasting one entry's mask (and id) per step.
-// The owner of a covered tile bumps its private running position (COUNT pass) and writes the id there
-// (SCATTER pass) - no ballots, no ranks: walking entries in order IS the stable order.
+// rectangle covers.  Two in-warp bit-matrix transposes flip the roles: lane t now OWNS local tiles t (rows
+// 0..3) and t + 32 (rows 4..7) and holds, per tile, the 32-bit set of entries that cover it, in list order.
+// COUNT pass: a popcount.  SCATTER pass: the owner walks its set bits in ascending order and appends the
+// ids (fetched from the entry's lane by shuffle) at its running position - walking the bits in order IS the
+// stable order.
 template <bool SCATTER>
 __global__ void __launch_bounds__(FINE_WARPS * 32)
     fine_kernel(const uint32_t* __restrict__ coarse_list, const uint2* __restrict__ coarse_ranges,
@@ -565,12 +588,21 @@ __global__ void __launch_bounds__(FINE_WARPS * 32)
 			run1 = __ldg(tile_start + (y + 4) * grid_x + x) + table[(size_t)sl * ST_TILES + 32 + lane];
 	}
 
-	for (uint32_t e0 = begin; e0 < end; e0 += 32) {
-		const uint32_t e = e0 + lane;
-		uint32_t id = 0, lo = 0, hi = 0;
+	// both 32-entry chunks of the slice are fetched up front (id -> rectangle is a dependent gather)
+	constexpr int CHUNKS = FINE_SLICE / 32;
+	uint32_t ids[CHUNKS], los[CHUNKS], his[CHUNKS];
+#pragma unroll
+	for (int c = 0; c < CHUNKS; c++) {
+		const uint32_t e = begin + 32 * c + lane;
+		ids[c] = (e < end) ? __ldg(coarse_list + e) : 0u;
+	}
+#pragma unroll
+	for (int c = 0; c < CHUNKS; c++) {
+		const uint32_t e = begin + 32 * c + lane;
+		los[c] = 0;
+		his[c] = 0;
 		if (e < end) {
-			id = __ldg(coarse_list + e);
-			const uint2 r = __ldg(rect + id);
+			const uint2 r = __ldg(rect + ids[c]);
 			const int x0 = (int)(r.x & 0xffffu) - (int)tx0, x1 = (int)(r.x >> 16) - (int)tx0;
 			const int y0 = (int)(r.y & 0xffffu) - (int)ty0, y1 = (int)(r.y >> 16) - (int)ty0;
 			const uint32_t cx0 = (uint32_t)max(x0, 0), cx1 = (uint32_t)min(x1, 8);
@@ -578,36 +610,39 @@ __global__ void __launch_bounds__(FINE_WARPS * 32)
 			if (cx1 > cx0 && cy1 > cy0) {
 				const uint32_t cols = ((1u << cx1) - (1u << cx0)) & 0xffu;
 				const uint32_t rows = ((1u << cy1) - (1u << cy0)) & 0xffu;
-				lo = cols * spread4(rows & 15u);
-				hi = cols * spread4(rows >> 4);
+				los[c] = cols * spread4(rows & 15u);
+				his[c] = cols * spread4(rows >> 4);
 			}
 		}
-		const uint32_t cnt = min(32u, end - e0);
+	}
+#pragma unroll
+	for (int c = 0; c < CHUNKS; c++) {
+		if (begin + 32 * c >= end)
+			break;
+		// bit j of m0 / m1: entry j of this chunk covers this lane's tile (rows 0..3 / rows 4..7)
+		uint32_t m0 = transpose32(los[c], lane), m1 = transpose32(his[c], lane);
 		if (SCATTER) {
-#pragma unroll 8
-			for (uint32_t j = 0; j < cnt; j++) {
-				const uint32_t mlo = __shfl_sync(0xffffffffu, lo, j);
-				const uint32_t mhi = __shfl_sync(0xffffffffu, hi, j);
-				const uint32_t idj = __shfl_sync(0xffffffffu, id, j);
-				if ((mlo >> lane) & 1u) {
+			const uint32_t most = __reduce_max_sync(0xffffffffu, max(__popc(m0), __popc(m1)));
+			for (uint32_t it = 0; it < most; it++) {
+				const uint32_t j0 = m0 ? (uint32_t)__ffs(m0) - 1u : 0u, j1 = m1 ? (uint32_t)__ffs(m1) - 1u : 0u;
+				const uint32_t id0 = __shfl_sync(0xffffffffu, ids[c], j0);
+				const uint32_t id1 = __shfl_sync(0xffffffffu, ids[c], j1);
+				if (m0) {
 					if (run0 < R_cap)
-						point_list[run0] = idj;
+						point_list[run0] = id0;
 					run0++;
+					m0 &= m0 - 1u;
 				}
-				if ((mhi >> lane) & 1u) {
+				if (m1) {
 					if (run1 < R_cap)
-						point_list[run1] = idj;
+						point_list[run1] = id1;
 					run1++;
+					m1 &= m1 - 1u;
 				}
 			}
 		} else {
-#pragma unroll 8
-			for (uint32_t j = 0; j < cnt; j++) {
-				const uint32_t mlo = __shfl_sync(0xffffffffu, lo, j);
-				const uint32_t mhi = __shfl_sync(0xffffffffu, hi, j);
-				run0 += (mlo >> lane) & 1u;
-				run1 += (mhi >> lane) & 1u;
-			}
+			run0 += __popc(m0);
+			run1 += __popc(m1);
 		}
 	}
 	if (!SCATTER) {

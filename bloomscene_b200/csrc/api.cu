@@ -768,6 +768,20 @@ void brs_forward_stats(long long* out, int reset)
 	}
 }
 
+int brs_get_marks(int P, int image_width, int image_height, uint32_t* out)
+{
+	int dev = 0;
+	Marks m;
+	if (cudaGetDevice(&dev) != cudaSuccess || !lookup_marks(MarksKey{dev, P, image_width, image_height}, m))
+		return 0;
+	if (out != nullptr) {
+		out[0] = m.R;
+		out[1] = m.R1;
+		out[2] = m.key_bits;
+	}
+	return 1;
+}
+
 void brs_reset_marks(void)
 {
 	std::lock_guard<std::mutex> lock(g_marks_mutex);

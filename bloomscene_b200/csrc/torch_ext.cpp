@@ -551,6 +551,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 		brs_note_counts(P, W, H, reinterpret_cast<const uint32_t*>(report.data_ptr<int>()));
 	});
 	m.def("reset_marks", []() { brs_reset_marks(); });
+	m.def("has_marks", [](int P, int W, int H) { return brs_get_marks(P, W, H, nullptr) != 0; });
 	m.def("forward_stats", [](bool reset) {
 		long long v[4];
 		brs_forward_stats(v, reset ? 1 : 0);

@@ -233,7 +233,9 @@ def bind(_C) -> SimpleNamespace:
         one view's preprocess / sort / binning kernels and its host wait for the instance count run under
         another view's blend; with `host_threads` every stream is driven by its own host thread (the native
         forward releases the GIL).  Returns (color [B,3,H,W], depth [B,1,H,W], radii list or None); every view's
-        result is bit-identical to a single `GaussianRasterizer` call with the same settings."""
+        result is bit-identical to a single `GaussianRasterizer` call with the same settings.  The call returns
+        after ONE host synchronisation for the whole batch (the reference waits once per frame,
+        rasterizer_impl.cu:282), plus one for the first frame of a (P, W, H) shape it has never seen."""
         views = list(raster_settings_list)
         if (shs is None) == (colors_precomp is None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
@@ -250,12 +252,24 @@ def bind(_C) -> SimpleNamespace:
         m3, op = means3D.detach(), opacities.detach()
         sh_, cp_, sc_, ro_, cv_ = opt(shs), opt(colors_precomp), opt(scales), opt(rotations), opt(cov3D_precomp)
 
-        def one(j, rs):
+        # Native module with brs_fwd_options: every view is a DEFERRED forward (no host wait at all; buffers sized
+        # from the high-water marks of this shape); the instance counts land in pinned host memory and are
+        # checked ONCE for the whole batch.  A view whose capacities were too small is rendered again in EXACT
+        # mode.  Any other module (the reference build): one plain call per view.
+        deferred = hasattr(_C, "rasterize_gaussians_ex") and dev.type == "cuda" and B > 0
+        reports = torch.zeros((B, 8), dtype=torch.int32).pin_memory() if deferred else None
+
+        def one(j, rs, exact=False):
             if (rs.image_height, rs.image_width) != (H, W):
                 raise Exception('render_views: all views of a batch must share one resolution')
-            out = _C.rasterize_gaussians(rs.bg, m3, cp_, op, sc_, ro_, rs.scale_modifier, cv_, rs.viewmatrix,
-                                         rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh_,
-                                         rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+            args = (rs.bg, m3, cp_, op, sc_, ro_, rs.scale_modifier, cv_, rs.viewmatrix, rs.projmatrix, rs.tanfovx,
+                    rs.tanfovy, rs.image_height, rs.image_width, sh_, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+            if deferred and not exact:
+                out = _C.rasterize_gaussians_ex(*args, _C.FWD_DEFERRED, 0, 0, 0, reports[j])
+            elif deferred:
+                out = _C.rasterize_gaussians_ex(*args, _C.FWD_EXACT, 0, 0, 0, None)
+            else:
+                out = _C.rasterize_gaussians(*args)
             color[j].copy_(out[1])
             depth[j].copy_(out[2])
             if keep_radii:
@@ -263,9 +277,13 @@ def bind(_C) -> SimpleNamespace:
 
         with torch.no_grad():
             n_lanes = max(1, min(int(streams), B)) if dev.type == "cuda" else 1
+            first = 0
+            if deferred and not _C.has_marks(m3.shape[0], W, H):
+                one(0, views[0], exact=True)  # a shape never seen before: one EXACT forward seeds its high-water marks
+                first = 1
             if n_lanes == 1:
-                for j, rs in enumerate(views):
-                    one(j, rs)
+                for j in range(first, B):
+                    one(j, views[j])
             else:
                 cur = torch.cuda.current_stream(dev)
                 lanes = lane_streams(dev, n_lanes)
@@ -273,8 +291,8 @@ def bind(_C) -> SimpleNamespace:
                     st.wait_stream(cur)  # inputs and the output stacks were produced on the caller's stream
 
                 def drive(lane):  # one host thread per stream: the native forward releases the GIL while it
-                    with torch.no_grad(), torch.cuda.stream(lanes[lane]):  # waits and launches
-                        for j in range(lane, B, n_lanes):
+                    with torch.no_grad(), torch.cuda.stream(lanes[lane]):  # launches (and, non-deferred, waits)
+                        for j in range(first + lane, B, n_lanes):
                             one(j, views[j])
 
                 if host_threads:
@@ -282,14 +300,21 @@ def bind(_C) -> SimpleNamespace:
                     for f in [pool.submit(drive, lane) for lane in range(n_lanes)]:
                         f.result()
                 else:
-                    for j, rs in enumerate(views):
-                        with torch.cuda.stream(lanes[j % n_lanes]):
-                            one(j, rs)
+                    for j in range(first, B):
+                        with torch.cuda.stream(lanes[(j - first) % n_lanes]):
+                            one(j, views[j])
                 for st in lanes:
                     cur.wait_stream(st)
                 if keep_radii:
-                    for r in radii:
+                    for r in radii[first:]:
                         r.record_stream(cur)  # allocated on a lane stream, consumed on the caller's
+            if deferred:
+                # the one host wait of the batch: every report has landed once the caller's stream is drained
+                torch.cuda.current_stream(dev).synchronize()
+                for j in range(first, B):
+                    _C.note_counts(m3.shape[0], W, H, reports[j])
+                    if int(reports[j, 5]) != 0:
+                        one(j, views[j], exact=True)
         return color, depth, radii
 
     return SimpleNamespace(

@@ -171,6 +171,9 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g,
                    brs_fwd_state* state, const brs_fwd_options* opt, brs_stream stream);
 /* Feeds the counts of a DEFERRED forward's report back into the high-water marks of its shape. */
 void brs_note_counts(int P, int image_width, int image_height, const uint32_t* report);
+/* High-water marks of a shape on the current device: returns 1 and fills out[3] = {R, R1, depth-key bits} if a
+ * forward of that shape has been seen, else 0. */
+int brs_get_marks(int P, int image_width, int image_height, uint32_t* out);
 /* Per calling thread: out[0] = EXACT forwards, out[1] = optimistic ones, out[2] = of those, re-run because a
  * capacity overflowed, out[3] = DEFERRED ones. */
 void brs_forward_stats(long long* out, int reset);

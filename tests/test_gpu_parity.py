@@ -534,3 +534,79 @@ def test_forward_modes_are_bit_identical_and_an_overflow_reruns():
     assert int(report[5]) & 3 == 3 and int(report[0]) == exact[0]
     assert torch.isfinite(tiny[1]).all()
     _C.reset_marks()
+
+
+def test_render_views_deferred_batch_recovers_from_overflow_and_replays_in_a_cuda_graph():
+    """render_views issues DEFERRED forwards (one host wait per batch).  (1) With stale high-water marks most
+    views overflow their capacities and must be re-rendered exactly; (2) a DEFERRED forward + backward is free of
+    host synchronisation, so it can be captured in a CUDA graph and replayed with new camera contents."""
+    api = pl.ours()
+    _C = api._C
+    scene = synthetic.make_scene(30_000, "band", "precomp", -4.4, seed=5).to(DEV)
+    W, H = 256, 160
+    cams = [synthetic.yaw_camera(W, H, 0.9 * k).to(DEV) for k in range(7)]
+    bg = torch.tensor([0.05, 0.1, 0.2], device=DEV)
+    mk = lambda mod: [synthetic.raster_settings(c, 0, bg, api.GaussianRasterizationSettings, scale_modifier=mod) for c in cams]
+    kw = dict(colors_precomp=scene.colors_precomp, scales=scene.scales, rotations=scene.rotations, keep_radii=True)
+
+    def singles(settings):
+        outs = []
+        with torch.no_grad():
+            for rs in settings:
+                outs.append(api.GaussianRasterizer(rs)(scene.means3D, torch.zeros_like(scene.means3D), scene.opacities,
+                                                       colors_precomp=scene.colors_precomp, scales=scene.scales,
+                                                       rotations=scene.rotations))
+        return outs
+
+    _C.reset_marks()
+    small = api.render_views(mk(0.5), scene.means3D, scene.opacities, streams=3, **kw)  # seeds small marks
+    _C.forward_stats(True)
+    # ~36x the instances: overflows (one host thread, so that this thread's counters see every forward)
+    big = api.render_views(mk(3.0), scene.means3D, scene.opacities, streams=3, host_threads=False, **kw)
+    st = _C.forward_stats(False)
+    assert st["deferred"] == len(cams) and st["exact"] >= 1, st
+    for settings, got in ((mk(0.5), small), (mk(3.0), big)):
+        for k, (c, r, d) in enumerate(singles(settings)):
+            assert torch.equal(c, got[0][k]) and torch.equal(d, got[1][k]) and torch.equal(r, got[2][k]), k
+
+    # CUDA graph: capture one deferred forward + backward on static buffers, replay it for another camera
+    Wc, _ = (t.to(DEV) for t in synthetic.loss_weights(W, H))
+    e = torch.Tensor([])
+    view, proj, campos = (cams[0].viewmatrix.clone(), cams[0].projmatrix.clone(), cams[0].campos.clone())
+    report = torch.zeros(8, dtype=torch.int32).pin_memory()
+    ref_report = torch.zeros(8, dtype=torch.int32).pin_memory()
+    cam0 = cams[0]
+
+    def fwd_bwd(rep):
+        fw = _C.rasterize_gaussians_ex(bg, scene.means3D, scene.colors_precomp, scene.opacities, scene.scales, scene.rotations,
+                                       1.0, e, view, proj, cam0.tanfovx, cam0.tanfovy, H, W, e, 0, campos, False, False,
+                                       _C.FWD_DEFERRED, 0, 0, 0, rep)
+        g = _C.rasterize_gaussians_backward(bg, scene.means3D, fw[3], scene.colors_precomp, scene.scales, scene.rotations, 1.0,
+                                            e, view, proj, cam0.tanfovx, cam0.tanfovy, Wc, e, e, 0, campos, fw[4], fw[0], fw[5],
+                                            fw[6], False)
+        return fw[1], fw[2], g[3], g[6]  # colour, depth, dL_dmeans3D, dL_dscales
+
+    api.render_views(mk(1.0), scene.means3D, scene.opacities, streams=1, **kw)  # marks for scale modifier 1
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fwd_bwd(report)  # warm-up outside the capture
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = fwd_bwd(report)
+    for k in (3, 5):
+        view.copy_(cams[k].viewmatrix)
+        proj.copy_(cams[k].projmatrix)
+        campos.copy_(cams[k].campos)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert int(report[5]) == 0
+        got = [t.clone() for t in static_out]
+        want = fwd_bwd(ref_report)
+        torch.cuda.synchronize()
+        assert int(report[0]) == int(ref_report[0]) > 0
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert pl.rel_l2(got[2], want[2]) <= 1e-5 and pl.rel_l2(got[3], want[3]) <= 1e-5
+    _C.reset_marks()

@@ -430,7 +430,7 @@ namespace {
 
 // High-water marks of the instance counts per (device, P, W, H): what sizes an optimistic forward.
 struct Marks {
-	uint32_t R = 0, R1 = 0, key_bits = 0;
+	uint32_t R = 0, R1 = 0, key_bits = 0, V = 0;
 };
 struct MarksKey {
 	int dev, P, W, H;
@@ -451,7 +451,7 @@ bool lookup_marks(const MarksKey& k, Marks& out)
 	out = it->second;
 	return true;
 }
-void raise_marks(const MarksKey& k, uint32_t R, uint32_t R1, uint32_t key_bits)
+void raise_marks(const MarksKey& k, uint32_t R, uint32_t R1, uint32_t key_bits, uint32_t V)
 {
 	std::lock_guard<std::mutex> lock(g_marks_mutex);
 	if (g_marks.size() >= 256 && g_marks.find(k) == g_marks.end())
@@ -460,6 +460,7 @@ void raise_marks(const MarksKey& k, uint32_t R, uint32_t R1, uint32_t key_bits)
 	m.R = R > m.R ? R : m.R;
 	m.R1 = R1 > m.R1 ? R1 : m.R1;
 	m.key_bits = key_bits > m.key_bits ? key_bits : m.key_bits;
+	m.V = V > m.V ? V : m.V;
 }
 
 struct Caps {
@@ -686,14 +687,16 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 	pa.depth_key = reinterpret_cast<uint32_t*>(c.geom + c.gl.depth_key);
 	pa.rect = reinterpret_cast<uint2*>(c.geom + c.gl.rect);
 	pa.total_tiles = hdr;
-	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
-
-	// ---- deferred: the caller's capacities (or the high-water marks), no host wait at all ----
 	int dev = 0;
 	BRS_CUDA(cudaGetDevice(&dev));
 	const MarksKey key{dev, P, W, H};
 	Marks marks;
 	const bool have_marks = lookup_marks(key, marks);
+	// SH rows: requested for all Gaussians up front when most of them were visible in the last views of this shape
+	pa.eager_sh = (have_marks && 2ull * marks.V > (unsigned long long)P) ? 1 : 0;
+	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
+
+	// ---- deferred: the caller's capacities (or the high-water marks), no host wait at all ----
 	if (mode == BRS_FWD_DEFERRED) {
 		Caps caps = caps_from_marks(marks); // zero marks -> the 4096-instance floor
 		if (opt->R_cap > 0)
@@ -725,7 +728,7 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 		counts_known = true;
 		if (t_slot.pinned[HDR_OVERFLOW] == 0) {
 			state->num_rendered = (int)t_slot.pinned[HDR_R];
-			raise_marks(key, t_slot.pinned[HDR_R], t_slot.pinned[HDR_R1], t_slot.pinned[HDR_KEY_BITS]);
+			raise_marks(key, t_slot.pinned[HDR_R], t_slot.pinned[HDR_R1], t_slot.pinned[HDR_KEY_BITS], t_slot.pinned[HDR_V]);
 			return BRS_OK;
 		}
 		// a capacity was too small: what was enqueued is memory-safe but wrong; run it again with the exact sizes
@@ -754,7 +757,7 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 	caps.R1_cap = R1;
 	caps.depth_passes = passes_for_bits(key_bits);
 	state->num_rendered = (int)R;
-	raise_marks(key, R, R1, key_bits);
+	raise_marks(key, R, R1, key_bits, V);
 	return enqueue_binning_and_blend(c, caps, nullptr, nullptr);
 }
 
@@ -793,7 +796,7 @@ void brs_note_counts(int P, int image_width, int image_height, const uint32_t* r
 	int dev = 0;
 	if (report == nullptr || cudaGetDevice(&dev) != cudaSuccess)
 		return;
-	raise_marks(MarksKey{dev, P, image_width, image_height}, report[HDR_R], report[HDR_R1], report[HDR_KEY_BITS]);
+	raise_marks(MarksKey{dev, P, image_width, image_height}, report[HDR_R], report[HDR_R1], report[HDR_KEY_BITS], report[HDR_V]);
 }
 
 int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii, const brs_fwd_state* state,
@@ -900,6 +903,14 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 	pb.accum = accum;
 	pb.accumulate = acc ? 1 : 0;
 	pb.depth_gradient = depth_grad ? 1 : 0;
+	{
+		int dev = 0;
+		Marks marks;
+		pb.eager_sh = (cudaGetDevice(&dev) == cudaSuccess && lookup_marks(MarksKey{dev, P, W, H}, marks) &&
+		               2ull * marks.V > (unsigned long long)P)
+		                  ? 1
+		                  : 0;
+	}
 	pb.dL_dmeans2D = grads->dL_dmeans2D;
 	pb.dL_dcolors = grads->dL_dcolors;
 	pb.dL_dopacity = grads->dL_dopacity;

@@ -707,13 +707,16 @@ __global__ void __launch_bounds__(256)
 	const uint32_t num_tiles = grid_x * grid_y;
 	const uint32_t chunk = (num_tiles + 255) / 256;
 	const uint32_t t0 = min(threadIdx.x * chunk, num_tiles), t1 = min(t0 + chunk, num_tiles);
+	// (plain L2 loads after the fence: unlike volatile ones they are issued back to back)
 	uint32_t local = 0;
+#pragma unroll 8
 	for (uint32_t i = t0; i < t1; i++)
-		local += ld_relaxed(tile_count + i);
+		local += __ldcg(tile_count + i);
 	uint32_t grand;
 	uint32_t start = block_exclusive_scan_256(local, s_warp, grand);
+#pragma unroll 8
 	for (uint32_t i = t0; i < t1; i++) {
-		const uint32_t v = ld_relaxed(tile_count + i);
+		const uint32_t v = __ldcg(tile_count + i);
 		tile_start[i] = start;
 		ranges[i] = v ? make_uint2(min(start, R_cap), min(start + v, R_cap)) : make_uint2(0u, 0u);
 		start += v;

@@ -26,6 +26,7 @@ struct PreprocessArgs {
 	float tan_fovx, tan_fovy, focal_x, focal_y;
 	uint32_t grid_x, grid_y;
 	int prefiltered;
+	int eager_sh;         // request every Gaussian's SH row up front (most are visible) instead of the visible ones' later
 	// outputs
 	int* radii;
 	float4* records;      // [3P]
@@ -189,6 +190,7 @@ struct PreprocessBwdArgs {
 	const float* accum; // [P][12] from the blend backward
 	int accumulate;     // 0: every output element is written; 1: see brs_grads.accumulate
 	int depth_gradient; // 1: accum slot 9 holds dL_dz (view-space depth) and feeds dL_dmeans3D
+	int eager_sh;       // request every Gaussian's SH row up front (most were rendered) instead of the rendered ones' later
 	int fact_offset;    // (set by the launcher) float offset of the basis-factor rows in dynamic shared memory
 	// outputs
 	float* dL_dmeans2D;   // [P,3]

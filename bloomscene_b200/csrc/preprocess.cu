@@ -62,14 +62,42 @@ struct Geometry {
 	uint2 rect_min, rect_max;
 };
 
+// The per-Gaussian inputs of the geometry half, fetched up front so that all loads of a thread are in
+// flight together (fetched where the reference reads them, behind the frustum test, each group would
+// expose its own DRAM latency).
+struct GeomInputs {
+	float3 mean;
+	float cov3D[6];
+};
+__device__ __forceinline__ GeomInputs load_geom_inputs(const float* means3D, const float* scales, int scales_stride,
+                                                       const float* rotations, const float* cov3D_precomp, int idx,
+                                                       float scale_modifier)
+{
+	GeomInputs in;
+	const float* mp = means3D + 3 * (size_t)idx;
+	in.mean = {__ldg(mp), __ldg(mp + 1), __ldg(mp + 2)};
+	if (cov3D_precomp != nullptr) {
+#pragma unroll
+		for (int i = 0; i < 6; i++)
+			in.cov3D[i] = __ldg(cov3D_precomp + 6 * (size_t)idx + i);
+	} else {
+		const float* sp = scales + (size_t)idx * scales_stride;
+		v3 s = make_v3(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2));
+		const float* rp = rotations + 4 * (size_t)idx;
+		float4 q = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
+		compute_cov3d(s, scale_modifier, q, in.cov3D); // reference forward.cu:118-152 (after its frustum test; no side effects)
+	}
+	return in;
+}
+
 // Everything of preprocessCUDA up to the tile rectangle (forward.cu:186-237). Returns false when
 // the reference would `return` early (culled / degenerate / zero-area rectangle).
-__device__ __forceinline__ bool compute_geometry(const float3 p_orig, const float* scales, int scales_stride,
-                                                 const float* rotations, const float* cov3D_precomp, int idx,
-                                                 float scale_modifier, const float* view, const float* proj, int W,
+__device__ __forceinline__ bool compute_geometry(const GeomInputs& in, const float* view, const float* proj, int W,
                                                  int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y,
                                                  uint32_t grid_x, uint32_t grid_y, bool prefiltered, Geometry& g)
 {
+	const float3 p_orig = in.mean;
+	const float* cov3D = in.cov3D;
 	// in_frustum (auxiliary.h:139-164): only the view-space z test is live.
 	float3 p_view = transform_point_4x3(p_orig, view);
 	if (p_view.z <= 0.2f) {
@@ -83,19 +111,6 @@ __device__ __forceinline__ bool compute_geometry(const float3 p_orig, const floa
 	float4 p_hom = transform_point_4x4(p_orig, proj);
 	float p_w = 1.0f / (p_hom.w + 0.0000001f);
 	float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
-
-	float cov3D[6];
-	if (cov3D_precomp != nullptr) {
-#pragma unroll
-		for (int i = 0; i < 6; i++)
-			cov3D[i] = __ldg(cov3D_precomp + 6 * (size_t)idx + i);
-	} else {
-		const float* sp = scales + (size_t)idx * scales_stride;
-		v3 s = make_v3(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2));
-		const float* rp = rotations + 4 * (size_t)idx;
-		float4 q = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
-		compute_cov3d(s, scale_modifier, q, cov3D);
-	}
 
 	float3 cov = compute_cov2d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, view);
 
@@ -169,32 +184,60 @@ __device__ __forceinline__ void stage_camera(float* s_cam, const float* view, co
 		s_cam[t] = __ldg(campos + t - 32);
 }
 
-// VEC: rows are 16 coefficient triples (48 floats = 12 float4) and `shs` is 16-byte aligned.
-template <bool VEC>
+// VEC: rows are 16 coefficient triples (48 floats = 12 float4 = 192 bytes) and `shs` is 16-byte aligned.  Every
+//   lane then fetches ITS row with one bulk asynchronous copy (cp.async.bulk -> SASS UBLKCP) into a pitch-13
+//   float4 shared-memory tile (lane-consecutive LDS.128 rows are conflict-free); the bytes are collected by one
+//   mbarrier per warp, so there is no block barrier between the geometry, load and evaluation phases and no
+//   SH data passes through registers on its way in.
+// EAGER: the rows of ALL 32 Gaussians of the warp are requested at the very start, together with the
+//   geometry inputs, so that a thread exposes one DRAM round trip instead of two; otherwise only the rows of
+//   the visible Gaussians are requested, after the geometry phase.  The host picks EAGER when the last views
+//   of this shape had most Gaussians visible (the rows of culled Gaussians are wasted traffic).
+template <bool VEC, bool EAGER>
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs a)
 {
 	extern __shared__ float4 s_dyn[]; // SH staging (only when a.shs != nullptr)
 	__shared__ float s_cam[36];
 	__shared__ uint32_t s_tiles[5][PRE_THREADS / 32];
+	__shared__ uint64_t s_bar[PRE_THREADS / 32];
 
+	const int block_first = blockIdx.x * PRE_THREADS;
+	const int idx = block_first + threadIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool in_range = idx < a.P;
+	const bool bulk = VEC && a.shs != nullptr;
+
+	if (bulk) {
+		if (lane == 0)
+			mbar_init(&s_bar[warp], 1);
+		__syncwarp();
+		if (EAGER) {
+			const uint32_t rows = (uint32_t)max(0, min(32, a.P - (block_first + 32 * warp)));
+			if (in_range)
+				bulk_copy_g2s(s_dyn + threadIdx.x * 13, a.shs + (size_t)idx * 48, 192u, &s_bar[warp]);
+			if (lane == 0)
+				mbar_arrive_expect_tx(&s_bar[warp], 192u * rows);
+		}
+	}
+	// all per-Gaussian geometry inputs and the opacity are requested before anything is computed
+	GeomInputs in;
+	float opacity = 0.f;
+	if (in_range) {
+		in = load_geom_inputs(a.means3D, a.scales, 3, a.rotations, a.cov3D_precomp, idx, a.scale_modifier);
+		opacity = __ldg(a.opacities + idx);
+	}
 	stage_camera(s_cam, a.viewmatrix, a.projmatrix, a.campos);
 	__syncthreads();
 	const float* view = s_cam;
 	const float* proj = s_cam + 16;
 
-	const int block_first = blockIdx.x * PRE_THREADS;
-	const int idx = block_first + threadIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
 	Geometry g;
 	bool visible = false;
 	float3 p_orig = {0.f, 0.f, 0.f};
-	if (idx < a.P) {
-		const float* mp = a.means3D + 3 * (size_t)idx;
-		p_orig = {__ldg(mp), __ldg(mp + 1), __ldg(mp + 2)};
-		visible = compute_geometry(p_orig, a.scales, 3, a.rotations, a.cov3D_precomp, idx, a.scale_modifier, view, proj,
-		                           a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, a.grid_x, a.grid_y,
-		                           a.prefiltered != 0, g);
+	if (in_range) {
+		p_orig = in.mean;
+		visible = compute_geometry(in, view, proj, a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, a.grid_x,
+		                           a.grid_y, a.prefiltered != 0, g);
 	}
 
 	const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
@@ -213,16 +256,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 		const int row_f = 3 * a.M; // floats per Gaussian
 		const int warp_first = block_first + 32 * warp;
 		if (VEC) {
-			// 12 float4 per row, pitch 13 float4: lane-consecutive LDS.128 rows are conflict-free.
-			const float4* src = reinterpret_cast<const float4*>(a.shs) + (size_t)warp_first * 12;
-			float4* dst = s_dyn + 32 * warp * 13;
-#pragma unroll
-			for (int k = 0; k < 12; k++) {
-				const int f = lane + 32 * k;
-				const int row = f / 12, col = f - row * 12;
-				if ((vis_mask >> row) & 1u)
-					dst[row * 13 + col] = ldg_stream_f4(src + f);
+			if (!EAGER) {
+				if (visible)
+					bulk_copy_g2s(s_dyn + threadIdx.x * 13, a.shs + (size_t)idx * 48, 192u, &s_bar[warp]);
+				if (lane == 0)
+					mbar_arrive_expect_tx(&s_bar[warp], 192u * (uint32_t)__popc(vis_mask));
 			}
+			if (vis_mask != 0u || EAGER)
+				mbar_wait(&s_bar[warp], 0u);
 		} else {
 			const int pitch = row_f | 1; // odd pitch: conflict-free scalar reads
 			float* s_sh = reinterpret_cast<float*>(s_dyn) + 32 * warp * pitch;
@@ -233,8 +274,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 				if ((vis_mask >> row) & 1u)
 					s_sh[row * pitch + col] = __ldg(src + f);
 			}
+			__syncwarp();
 		}
-		__syncwarp();
 		if (visible) {
 			const v3 pos = make_v3(p_orig.x, p_orig.y, p_orig.z);
 			const v3 cam = make_v3(s_cam[32], s_cam[33], s_cam[34]);
@@ -256,7 +297,6 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	// ---- outputs ----
 	if (idx < a.P) {
 		if (visible) {
-			const float opacity = __ldg(a.opacities + idx);
 			const float tau = cull_tau(g.conic, opacity, g.radius);
 			float4* rec = a.records + 3 * (size_t)idx;
 			rec[0] = make_float4(g.xy.x, g.xy.y, tau, 0.f);
@@ -318,12 +358,10 @@ __global__ void __launch_bounds__(256) filter_kernel(FilterArgs a)
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= a.P)
 		return;
-	const float* mp = a.means3D + 3 * (size_t)idx;
-	float3 p_orig = {__ldg(mp), __ldg(mp + 1), __ldg(mp + 2)};
+	const GeomInputs in = load_geom_inputs(a.means3D, a.scales, a.scales_stride, a.rotations, a.cov3D_precomp, idx, a.scale_modifier);
 	Geometry g;
-	bool visible = compute_geometry(p_orig, a.scales, a.scales_stride, a.rotations, a.cov3D_precomp, idx,
-	                                a.scale_modifier, s_cam, s_cam + 16, a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x,
-	                                a.focal_y, a.grid_x, a.grid_y, a.prefiltered != 0, g);
+	bool visible = compute_geometry(in, s_cam, s_cam + 16, a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, a.grid_x,
+	                                a.grid_y, a.prefiltered != 0, g);
 	a.radii[idx] = visible ? g.radius : 0;
 }
 
@@ -358,10 +396,12 @@ cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream)
 		vec = (a.M == 16) && ((reinterpret_cast<uintptr_t>(a.shs) & 15u) == 0);
 		smem = vec ? (size_t)PRE_THREADS * 13 * sizeof(float4) : (size_t)PRE_THREADS * ((3 * a.M) | 1) * sizeof(float);
 	}
-	if (vec)
-		preprocess_kernel<true><<<blocks, PRE_THREADS, smem, stream>>>(a);
+	if (vec && a.eager_sh)
+		preprocess_kernel<true, true><<<blocks, PRE_THREADS, smem, stream>>>(a);
+	else if (vec)
+		preprocess_kernel<true, false><<<blocks, PRE_THREADS, smem, stream>>>(a);
 	else
-		preprocess_kernel<false><<<blocks, PRE_THREADS, smem, stream>>>(a);
+		preprocess_kernel<false, false><<<blocks, PRE_THREADS, smem, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
 }

@@ -23,7 +23,7 @@ BUILD = PKG / "_build"
 LIB = PKG / "libbloomrast.so"
 EXT = PKG / "_C.so"
 
-CU_SOURCES = ["preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu", "measure.cu", "api.cu"]
+CU_SOURCES = ["preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu", "loss.cu", "neural.cu", "measure.cu", "api.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3",
     "-gencode", "arch=compute_100a,code=sm_100a",

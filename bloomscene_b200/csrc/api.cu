@@ -924,6 +924,100 @@ int brs_backward(const brs_view* view, const brs_gaussians* g, const int* radii,
 	return BRS_OK;
 }
 
+size_t brs_l1_ssim_blocks(int C, int H, int W) { return (C > 0 && H > 0 && W > 0) ? l1_ssim_blocks(C, H, W) : 0; }
+
+int brs_l1_ssim_forward(const float* x, const float* y, int C, int H, int W, float* dmaps, float* partial, brs_stream stream)
+{
+	if (C < 0 || H < 0 || W < 0)
+		return BRS_ERR_INVALID_ARG;
+	if ((size_t)C * H * W == 0)
+		return BRS_OK;
+	if (x == nullptr || y == nullptr || dmaps == nullptr || partial == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	BRS_CUDA(launch_l1_ssim_forward(x, y, C, H, W, dmaps, partial, stream));
+	return BRS_OK;
+}
+
+int brs_l1_ssim_backward(const float* x, const float* y, const float* dmaps, int C, int H, int W, const float* dL_dloss,
+                         float lambda_dssim, float* dL_dx, brs_stream stream)
+{
+	if (C < 0 || H < 0 || W < 0)
+		return BRS_ERR_INVALID_ARG;
+	if ((size_t)C * H * W == 0)
+		return BRS_OK;
+	if (x == nullptr || y == nullptr || dmaps == nullptr || dL_dloss == nullptr || dL_dx == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	BRS_CUDA(launch_l1_ssim_backward(x, y, dmaps, C, H, W, dL_dloss, lambda_dssim, dL_dx, stream));
+	return BRS_OK;
+}
+
+size_t brs_neural_scratch_bytes(int N) { return neural_scratch_bytes(N < 0 ? 0 : N); }
+
+int brs_neural_gaussians_forward(const brs_neural_inputs* in, const brs_neural_outputs* out, void* scratch, brs_stream stream)
+{
+	if (in == nullptr || out == nullptr || in->N < 0 || in->K < 0 || out->count == nullptr || scratch == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	if (in->K > 32)
+		return BRS_ERR_UNSUPPORTED;
+	const bool empty = (size_t)in->N * in->K == 0;
+	if (!empty && (in->anchor == nullptr || in->grid_scaling == nullptr || in->offsets == nullptr || in->neural_opacity == nullptr ||
+	               in->color == nullptr || in->scale_rot == nullptr || out->xyz == nullptr || out->color == nullptr ||
+	               out->opacity == nullptr || out->scaling == nullptr || out->rot == nullptr || out->index == nullptr))
+		return BRS_ERR_INVALID_ARG;
+	NeuralFwdArgs a{};
+	a.N = empty ? 0 : in->N;
+	a.K = in->K;
+	a.anchor = in->anchor;
+	a.grid_scaling = in->grid_scaling;
+	a.offsets = in->offsets;
+	a.neural_opacity = in->neural_opacity;
+	a.color = in->color;
+	a.scale_rot = in->scale_rot;
+	a.xyz = out->xyz;
+	a.out_color = out->color;
+	a.out_opacity = out->opacity;
+	a.scaling = out->scaling;
+	a.rot = out->rot;
+	a.index = out->index;
+	a.count = out->count;
+	BRS_CUDA(launch_neural_forward(a, scratch, stream));
+	return BRS_OK;
+}
+
+int brs_neural_gaussians_backward(const brs_neural_inputs* in, const int* index, const brs_neural_grads* g, brs_stream stream)
+{
+	if (in == nullptr || g == nullptr || in->N < 0 || in->K < 0)
+		return BRS_ERR_INVALID_ARG;
+	if (in->K > 32)
+		return BRS_ERR_UNSUPPORTED;
+	if ((size_t)in->N * in->K == 0)
+		return BRS_OK;
+	if (index == nullptr || in->grid_scaling == nullptr || in->offsets == nullptr || in->scale_rot == nullptr ||
+	    g->d_anchor == nullptr || g->d_grid_scaling == nullptr || g->d_offsets == nullptr || g->d_neural_opacity == nullptr ||
+	    g->d_color_in == nullptr || g->d_scale_rot == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	NeuralBwdArgs a{};
+	a.N = in->N;
+	a.K = in->K;
+	a.grid_scaling = in->grid_scaling;
+	a.offsets = in->offsets;
+	a.scale_rot = in->scale_rot;
+	a.index = index;
+	a.d_xyz = g->d_xyz;
+	a.d_color = g->d_color;
+	a.d_opacity = g->d_opacity;
+	a.d_scaling = g->d_scaling;
+	a.d_rot = g->d_rot;
+	a.d_anchor = g->d_anchor;
+	a.d_grid_scaling = g->d_grid_scaling;
+	a.d_offsets = g->d_offsets;
+	a.d_neural_opacity = g->d_neural_opacity;
+	a.d_color_in = g->d_color_in;
+	a.d_scale_rot = g->d_scale_rot;
+	BRS_CUDA(launch_neural_backward(a, stream));
+	return BRS_OK;
+}
+
 int brs_visible_filter(const brs_view* view, int P, const float* means3D, const float* scales, int scales_stride,
                        const float* rotations, const float* cov3D_precomp, int* radii, brs_stream stream)
 {

@@ -204,6 +204,56 @@ struct PreprocessBwdArgs {
 };
 cudaError_t launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t stream);
 
+// ---- loss.cu: fused L1 + SSIM loss ------------------------------------------------
+size_t l1_ssim_blocks(int C, int H, int W); // number of (SSIM sum, L1 sum) pairs the forward writes
+cudaError_t launch_l1_ssim_forward(const float* x, const float* y, int C, int H, int W, float* dmaps /* [3][C][H][W] */,
+                                   float* partial /* [blocks][2] */, cudaStream_t stream);
+cudaError_t launch_l1_ssim_backward(const float* x, const float* y, const float* dmaps, int C, int H, int W,
+                                    const float* dL_dloss /* device scalar */, float lambda_dssim, float* dL_dx,
+                                    cudaStream_t stream);
+
+// ---- neural.cu: fused epilogue of the neural-Gaussian generation ---------------------
+struct NeuralFwdArgs {
+	int N, K;                    // anchors, offsets per anchor (K <= 32)
+	const float* anchor;         // [N,3]
+	const float* grid_scaling;   // [N,6]
+	const float* offsets;        // [N*K,3]
+	const float* neural_opacity; // [N*K]
+	const float* color;          // [N*K,3]
+	const float* scale_rot;      // [N*K,7]
+	// outputs, capacity N*K rows; rows [0, *count) are valid
+	float* xyz;         // [.,3]
+	float* out_color;   // [.,3]
+	float* out_opacity; // [.]
+	float* scaling;     // [.,3]
+	float* rot;         // [.,4]
+	int* index;         // [N*K]: output row of every input row, -1 where neural_opacity <= 0
+	uint32_t* count;    // device scalar: number of surviving rows
+	uint32_t* ticket;   // (set by the launcher)
+	uint32_t* status;   // (set by the launcher)
+};
+struct NeuralBwdArgs {
+	int N, K;
+	const float* grid_scaling;
+	const float* offsets;
+	const float* scale_rot;
+	const int* index;
+	const float* d_xyz;     // [M,3]
+	const float* d_color;   // [M,3]
+	const float* d_opacity; // [M]
+	const float* d_scaling; // [M,3]
+	const float* d_rot;     // [M,4]
+	float* d_anchor;         // [N,3]
+	float* d_grid_scaling;   // [N,6]
+	float* d_offsets;        // [N*K,3]
+	float* d_neural_opacity; // [N*K]
+	float* d_color_in;       // [N*K,3]
+	float* d_scale_rot;      // [N*K,7]
+};
+size_t neural_scratch_bytes(int N);
+cudaError_t launch_neural_forward(const NeuralFwdArgs& a, void* scratch, cudaStream_t stream);
+cudaError_t launch_neural_backward(const NeuralBwdArgs& a, cudaStream_t stream);
+
 // ---- measure.cu (bench / profiling only) ----------------------------------------------------------
 cudaError_t launch_count_pairs(const BlendFwdArgs& a, unsigned long long* out, cudaStream_t stream);
 double probe_fp32_tflops(cudaStream_t stream);

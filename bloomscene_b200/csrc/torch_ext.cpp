@@ -456,6 +456,134 @@ torch::Tensor RasterizeGaussiansfilterCUDA(const torch::Tensor& means3D, const t
 	return radii;
 }
 
+// ---- the steps either side of the rasterizer -----------------------------------------
+
+namespace {
+const float* f32_cuda(const torch::Tensor& t, torch::Tensor& keep, const char* name)
+{
+	TORCH_CHECK(t.defined() && t.is_cuda() && t.scalar_type() == torch::kFloat32, name, " must be a CUDA float32 tensor");
+	keep = t.contiguous();
+	return keep.data_ptr<float>();
+}
+} // namespace
+
+// (dmaps [3,C,H,W], partial [blocks,2]) of loss = (1 - l) mean|x - y| + l (1 - mean SSIM(x, y))
+std::tuple<torch::Tensor, torch::Tensor> L1SsimForward(const torch::Tensor& x, const torch::Tensor& y)
+{
+	TORCH_CHECK(x.dim() == 3 && x.sizes() == y.sizes(), "l1_ssim: image and target must both be [C,H,W]");
+	c10::cuda::CUDAGuard guard(x.device());
+	torch::Tensor k[2];
+	const float* xp = f32_cuda(x, k[0], "image");
+	const float* yp = f32_cuda(y, k[1], "target");
+	const int C = x.size(0), H = x.size(1), W = x.size(2);
+	torch::Tensor dmaps = torch::empty({3, C, H, W}, x.options());
+	torch::Tensor partial = torch::empty({(int64_t)brs_l1_ssim_blocks(C, H, W), 2}, x.options());
+	check_status(brs_l1_ssim_forward(xp, yp, C, H, W, dmaps.data_ptr<float>(), partial.data_ptr<float>(), current_stream()),
+	             "l1_ssim_forward");
+	return std::make_tuple(dmaps, partial);
+}
+
+torch::Tensor L1SsimBackward(const torch::Tensor& x, const torch::Tensor& y, const torch::Tensor& dmaps,
+                             const torch::Tensor& dL_dloss, double lambda_dssim)
+{
+	c10::cuda::CUDAGuard guard(x.device());
+	torch::Tensor k[4];
+	const float* xp = f32_cuda(x, k[0], "image");
+	const float* yp = f32_cuda(y, k[1], "target");
+	const float* dp = f32_cuda(dmaps, k[2], "dmaps");
+	const float* up = f32_cuda(dL_dloss, k[3], "dL_dloss");
+	TORCH_CHECK(dL_dloss.numel() == 1, "dL_dloss must be a scalar");
+	const int C = x.size(0), H = x.size(1), W = x.size(2);
+	torch::Tensor dx = torch::empty({C, H, W}, x.options());
+	check_status(brs_l1_ssim_backward(xp, yp, dp, C, H, W, up, (float)lambda_dssim, dx.data_ptr<float>(), current_stream()),
+	             "l1_ssim_backward");
+	return dx;
+}
+
+// (xyz, color, opacity, scaling, rot, index, count) with capacity N*K rows; count is a device int32 scalar
+std::vector<torch::Tensor> NeuralGaussiansForward(const torch::Tensor& anchor, const torch::Tensor& grid_scaling,
+                                                  const torch::Tensor& offsets, const torch::Tensor& neural_opacity,
+                                                  const torch::Tensor& color, const torch::Tensor& scale_rot)
+{
+	c10::cuda::CUDAGuard guard(anchor.device());
+	const int64_t N = anchor.size(0);
+	TORCH_CHECK(anchor.dim() == 2 && anchor.size(1) == 3 && grid_scaling.dim() == 2 && grid_scaling.size(0) == N && grid_scaling.size(1) == 6,
+	            "neural_gaussians: anchor [N,3], grid_scaling [N,6]");
+	const int64_t NK = neural_opacity.numel();
+	TORCH_CHECK(N == 0 ? NK == 0 : NK % N == 0, "neural_gaussians: neural_opacity must hold N*K values");
+	const int64_t K = N ? NK / N : 0;
+	TORCH_CHECK(offsets.numel() == NK * 3 && color.numel() == NK * 3 && scale_rot.numel() == NK * 7,
+	            "neural_gaussians: offsets [N*K,3], color [N*K,3], scale_rot [N*K,7]");
+	torch::Tensor k[6];
+	brs_neural_inputs in{};
+	in.N = (int)N;
+	in.K = (int)K;
+	in.anchor = f32_cuda(anchor, k[0], "anchor");
+	in.grid_scaling = f32_cuda(grid_scaling, k[1], "grid_scaling");
+	in.offsets = f32_cuda(offsets, k[2], "offsets");
+	in.neural_opacity = f32_cuda(neural_opacity, k[3], "neural_opacity");
+	in.color = f32_cuda(color, k[4], "color");
+	in.scale_rot = f32_cuda(scale_rot, k[5], "scale_rot");
+	auto fo = anchor.options().dtype(torch::kFloat32);
+	auto io = anchor.options().dtype(torch::kInt32);
+	torch::Tensor xyz = torch::empty({NK, 3}, fo), col = torch::empty({NK, 3}, fo), op = torch::empty({NK, 1}, fo),
+	              sc = torch::empty({NK, 3}, fo), rot = torch::empty({NK, 4}, fo), index = torch::empty({NK}, io),
+	              count = torch::empty({1}, io);
+	torch::Tensor scratch = torch::empty({(int64_t)brs_neural_scratch_bytes((int)N)}, anchor.options().dtype(torch::kByte));
+	brs_neural_outputs out{};
+	out.xyz = xyz.data_ptr<float>();
+	out.color = col.data_ptr<float>();
+	out.opacity = op.data_ptr<float>();
+	out.scaling = sc.data_ptr<float>();
+	out.rot = rot.data_ptr<float>();
+	out.index = index.data_ptr<int>();
+	out.count = reinterpret_cast<uint32_t*>(count.data_ptr<int>());
+	check_status(brs_neural_gaussians_forward(&in, &out, scratch.data_ptr(), current_stream()), "neural_gaussians_forward");
+	return {xyz, col, op, sc, rot, index, count};
+}
+
+std::vector<torch::Tensor> NeuralGaussiansBackward(const torch::Tensor& grid_scaling, const torch::Tensor& offsets,
+                                                   const torch::Tensor& scale_rot, const torch::Tensor& index,
+                                                   const torch::Tensor& d_xyz, const torch::Tensor& d_color,
+                                                   const torch::Tensor& d_opacity, const torch::Tensor& d_scaling,
+                                                   const torch::Tensor& d_rot)
+{
+	c10::cuda::CUDAGuard guard(grid_scaling.device());
+	const int64_t N = grid_scaling.size(0), NK = index.numel();
+	const int64_t K = N ? NK / N : 0;
+	torch::Tensor k[8];
+	brs_neural_inputs in{};
+	in.N = (int)N;
+	in.K = (int)K;
+	in.grid_scaling = f32_cuda(grid_scaling, k[0], "grid_scaling");
+	in.offsets = f32_cuda(offsets, k[1], "offsets");
+	in.scale_rot = f32_cuda(scale_rot, k[2], "scale_rot");
+	TORCH_CHECK(index.is_cuda() && index.scalar_type() == torch::kInt32 && index.is_contiguous(), "index: contiguous CUDA int32");
+	const int64_t M = d_xyz.size(0);
+	TORCH_CHECK(d_xyz.numel() == M * 3 && d_color.numel() == M * 3 && d_opacity.numel() == M && d_scaling.numel() == M * 3 &&
+	                d_rot.numel() == M * 4,
+	            "neural_gaussians_backward: upstream gradients must all have M rows");
+	auto fo = grid_scaling.options().dtype(torch::kFloat32);
+	torch::Tensor d_anchor = torch::empty({N, 3}, fo), d_gs = torch::empty({N, 6}, fo), d_off = torch::empty({NK, 3}, fo),
+	              d_nop = torch::empty({NK, 1}, fo), d_col = torch::empty({NK, 3}, fo), d_sr = torch::empty({NK, 7}, fo);
+	brs_neural_grads g{};
+	if (M > 0) {
+		g.d_xyz = f32_cuda(d_xyz, k[3], "d_xyz");
+		g.d_color = f32_cuda(d_color, k[4], "d_color");
+		g.d_opacity = f32_cuda(d_opacity, k[5], "d_opacity");
+		g.d_scaling = f32_cuda(d_scaling, k[6], "d_scaling");
+		g.d_rot = f32_cuda(d_rot, k[7], "d_rot");
+	}
+	g.d_anchor = d_anchor.data_ptr<float>();
+	g.d_grid_scaling = d_gs.data_ptr<float>();
+	g.d_offsets = d_off.data_ptr<float>();
+	g.d_neural_opacity = d_nop.data_ptr<float>();
+	g.d_color_in = d_col.data_ptr<float>();
+	g.d_scale_rot = d_sr.data_ptr<float>();
+	check_status(brs_neural_gaussians_backward(&in, index.data_ptr<int>(), &g, current_stream()), "neural_gaussians_backward");
+	return {d_anchor, d_gs, d_off, d_nop, d_col, d_sr};
+}
+
 // ---- extras used by tests / bench (not part of the reference surface) ----------------------------
 
 std::tuple<torch::Tensor, torch::Tensor> SortPairs(const torch::Tensor& keys, const c10::optional<torch::Tensor>& vals,
@@ -538,6 +666,10 @@ pybind11::dict StageTimes()
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 {
+	m.def("l1_ssim_forward", &L1SsimForward);
+	m.def("l1_ssim_backward", &L1SsimBackward);
+	m.def("neural_gaussians_forward", &NeuralGaussiansForward);
+	m.def("neural_gaussians_backward", &NeuralGaussiansBackward);
 	m.def("count_pairs", &CountPairs);
 	m.def("stage_timing", [](bool enable) { brs_stage_timing(enable ? 1 : 0); });
 	m.def("stage_times", &StageTimes);

@@ -244,6 +244,61 @@ int brs_version(void);
 /* Number of kernels this library launched on the calling thread since the last reset. */
 long long brs_launch_count(int reset);
 
+/* --- the steps either side of the rasterizer (extensions; opt-in) ------------------- */
+
+/* Fused photometric loss of the training step: loss = (1 - lambda) * mean|x - y| + lambda * (1 - mean SSIM(x, y)),
+ * replacing the torch-op chains of reference utils/loss.py:83-84 (l1_loss) and :91-135 (ssim: 11 x 11 Gaussian
+ * window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2) as used in bloomscene.py:284-287.
+ * Forward: x, y are [C,H,W]; writes the three derivative maps the backward needs into dmaps [3,C,H,W] and one
+ * (sum of SSIM, sum of |x - y|) pair per 16 x 16 block into partial [brs_l1_ssim_blocks()][2]; the caller sums
+ * them (deterministic) and forms the loss.  Backward: dL_dx [C,H,W] = *dL_dloss * d loss / d x. */
+size_t brs_l1_ssim_blocks(int C, int H, int W);
+int brs_l1_ssim_forward(const float* x, const float* y, int C, int H, int W, float* dmaps, float* partial, brs_stream stream);
+int brs_l1_ssim_backward(const float* x, const float* y, const float* dmaps, int C, int H, int W,
+                         const float* dL_dloss, float lambda_dssim, float* dL_dx, brs_stream stream);
+
+/* Fused epilogue of the neural-Gaussian generation, replacing the mask / concat / boolean-index / split /
+ * post-process chain of reference gaussian_renderer/__init__.py:168-203: for every (anchor n, offset k) row with
+ * neural_opacity > 0, in row order,
+ *   xyz = anchor[n] + offsets[n,k] * grid_scaling[n,:3]      scaling = grid_scaling[n,3:] * sigmoid(scale_rot[:3])
+ *   rot = normalize(scale_rot[3:7])                          colour, opacity copied
+ * written to the first *count rows of the output arrays (capacity N*K rows each); index[n*K+k] = output row or -1.
+ * `scratch` = brs_neural_scratch_bytes(N) bytes.  K <= 32.  Backward: all six input gradients, fully written. */
+typedef struct brs_neural_inputs {
+	int N, K;
+	const float* anchor;         /* [N,3]   */
+	const float* grid_scaling;   /* [N,6]   */
+	const float* offsets;        /* [N*K,3] */
+	const float* neural_opacity; /* [N*K]   */
+	const float* color;          /* [N*K,3] */
+	const float* scale_rot;      /* [N*K,7] */
+} brs_neural_inputs;
+typedef struct brs_neural_outputs {
+	float* xyz;      /* [N*K,3] */
+	float* color;    /* [N*K,3] */
+	float* opacity;  /* [N*K]   */
+	float* scaling;  /* [N*K,3] */
+	float* rot;      /* [N*K,4] */
+	int* index;      /* [N*K]   */
+	uint32_t* count; /* device scalar */
+} brs_neural_outputs;
+typedef struct brs_neural_grads {
+	const float* d_xyz;      /* [M,3] upstream */
+	const float* d_color;    /* [M,3] */
+	const float* d_opacity;  /* [M]   */
+	const float* d_scaling;  /* [M,3] */
+	const float* d_rot;      /* [M,4] */
+	float* d_anchor;         /* [N,3] outputs */
+	float* d_grid_scaling;   /* [N,6] */
+	float* d_offsets;        /* [N*K,3] */
+	float* d_neural_opacity; /* [N*K] */
+	float* d_color_in;       /* [N*K,3] */
+	float* d_scale_rot;      /* [N*K,7] */
+} brs_neural_grads;
+size_t brs_neural_scratch_bytes(int N);
+int brs_neural_gaussians_forward(const brs_neural_inputs* in, const brs_neural_outputs* out, void* scratch, brs_stream stream);
+int brs_neural_gaussians_backward(const brs_neural_inputs* in, const int* index, const brs_neural_grads* g, brs_stream stream);
+
 /* --- measurement hooks (bench / profiling only; off by default) ---------------------------- */
 
 /* Stage ids for brs_stage_times(). */

@@ -1,2 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-for c in A C D; do python tools/stage_times.py $c --bwd 2>&1 | tail -2; done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12

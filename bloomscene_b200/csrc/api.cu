@@ -1018,16 +1018,20 @@ int brs_neural_gaussians_backward(const brs_neural_inputs* in, const int* index,
 	return BRS_OK;
 }
 
-int brs_visible_filter(const brs_view* view, int P, const float* means3D, const float* scales, int scales_stride,
-                       const float* rotations, const float* cov3D_precomp, int* radii, brs_stream stream)
+static int visible_filter_impl(const brs_view* view, int P, const float* means3D, const float* scales, int scales_stride,
+                               const float* rotations, const float* cov3D_precomp, int* radii, long long* indices,
+                               uint32_t* count, void* scratch, brs_stream stream)
 {
 	int st = validate_view(view, false);
 	if (st != BRS_OK)
 		return st;
 	if (P < 0)
 		return BRS_ERR_INVALID_ARG;
-	if (P == 0)
+	if (P == 0) {
+		if (count != nullptr)
+			BRS_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), stream));
 		return BRS_OK;
+	}
 	const bool has_sr = scales != nullptr && rotations != nullptr;
 	if (means3D == nullptr || radii == nullptr || has_sr == (cov3D_precomp != nullptr) || (has_sr && scales_stride < 3))
 		return BRS_ERR_INVALID_ARG;
@@ -1052,8 +1056,34 @@ int brs_visible_filter(const brs_view* view, int P, const float* means3D, const 
 	fa.grid_y = (H + TILE_Y - 1) / TILE_Y;
 	fa.prefiltered = view->prefiltered;
 	fa.radii = radii;
+	if (indices != nullptr) {
+		BRS_CUDA(cudaMemsetAsync(scratch, 0, brs_filter_scratch_bytes(P), stream));
+		fa.indices = indices;
+		fa.count = count;
+		fa.ticket = static_cast<uint32_t*>(scratch);
+		fa.status = fa.ticket + 64;
+	}
 	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_filter(fa, stream), view->debug != 0, stream);
 	return BRS_OK;
+}
+
+size_t brs_filter_scratch_bytes(int P) { return align_up(256 + sizeof(uint32_t) * (size_t)((P < 0 ? 0 : P) / 256 + 1), 256); }
+
+int brs_visible_filter(const brs_view* view, int P, const float* means3D, const float* scales, int scales_stride,
+                       const float* rotations, const float* cov3D_precomp, int* radii, brs_stream stream)
+{
+	return visible_filter_impl(view, P, means3D, scales, scales_stride, rotations, cov3D_precomp, radii, nullptr, nullptr, nullptr,
+	                           stream);
+}
+
+int brs_visible_filter_compact(const brs_view* view, int P, const float* means3D, const float* scales, int scales_stride,
+                               const float* rotations, const float* cov3D_precomp, int* radii, long long* indices,
+                               uint32_t* count, void* scratch, brs_stream stream)
+{
+	if (indices == nullptr || count == nullptr || scratch == nullptr)
+		return BRS_ERR_INVALID_ARG;
+	return visible_filter_impl(view, P, means3D, scales, scales_stride, rotations, cov3D_precomp, radii, indices, count, scratch,
+	                           stream);
 }
 
 int brs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,

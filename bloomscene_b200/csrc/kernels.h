@@ -52,6 +52,11 @@ struct FilterArgs {
 	uint32_t grid_x, grid_y;
 	int prefiltered;
 	int* radii;
+	// compaction (optional: all four or none): ascending indices of the Gaussians with radii > 0 and their count
+	long long* indices; // [P]
+	uint32_t* count;    // device scalar
+	uint32_t* ticket;   // pre-zeroed
+	uint32_t* status;   // [ceil(P / 256)], pre-zeroed
 };
 cudaError_t launch_filter(const FilterArgs& a, cudaStream_t stream);
 cudaError_t launch_check_frustum(int P, const float* means3D, const float* viewmatrix, uint8_t* present,

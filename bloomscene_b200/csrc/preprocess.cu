@@ -365,6 +365,86 @@ __global__ void __launch_bounds__(256) filter_kernel(FilterArgs a)
 	a.radii[idx] = visible ? g.radius : 0;
 }
 
+// K10 fused with the compaction its caller does next: BloomScene turns the radii into
+// visible_mask = radii > 0 and boolean-indexes anchors, features, offsets, scalings with it
+// (gaussian_renderer/__init__.py:294-349, :39-60) - one torch nonzero (and one host synchronisation) per
+// indexed tensor.  This kernel also writes the ascending list of visible indices and their count, so the caller
+// gathers with index_select after a single read of the count.  Order-preserving compaction: block scan +
+// decoupled look-back over blocks (tickets handed out in order).
+__global__ void __launch_bounds__(256) filter_compact_kernel(FilterArgs a)
+{
+	__shared__ float s_cam[36];
+	__shared__ uint32_t s_warp[8];
+	__shared__ uint32_t s_bcast[2];
+	constexpr uint32_t F_LOCAL = 1u << 30, F_INCL = 2u << 30, F_MASK = 3u << 30;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0)
+		s_bcast[0] = atomicAdd(a.ticket, 1u);
+	stage_camera(s_cam, a.viewmatrix, a.projmatrix, nullptr);
+	__syncthreads();
+	const uint32_t blk = s_bcast[0];
+	const int idx = (int)(blk * 256 + tid);
+	bool visible = false;
+	if (idx < a.P) {
+		const GeomInputs in = load_geom_inputs(a.means3D, a.scales, a.scales_stride, a.rotations, a.cov3D_precomp, idx, a.scale_modifier);
+		Geometry g;
+		visible = compute_geometry(in, s_cam, s_cam + 16, a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, a.grid_x,
+		                           a.grid_y, a.prefiltered != 0, g);
+		a.radii[idx] = visible ? g.radius : 0;
+	}
+	const uint32_t vmask = __ballot_sync(0xffffffffu, visible);
+	if (lane == 0)
+		s_warp[warp] = __popc(vmask);
+	__syncthreads();
+	uint32_t warp_off = 0, block_total = 0;
+#pragma unroll
+	for (int w = 0; w < 8; w++) {
+		if ((uint32_t)w < warp)
+			warp_off += s_warp[w];
+		block_total += s_warp[w];
+	}
+	if (warp == 0) {
+		if (lane == 0) {
+			const uint32_t v = (blk == 0 ? F_INCL : F_LOCAL) | block_total;
+			asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.status + blk), "r"(v) : "memory");
+		}
+		uint32_t excl = 0;
+		int p = (int)blk - 1;
+		while (p >= 0) {
+			const int q = p - (int)lane;
+			uint32_t v = F_INCL;
+			if (q >= 0)
+				asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.status + q) : "memory");
+			const uint32_t f = v & F_MASK;
+			const uint32_t not_ready = __ballot_sync(0xffffffffu, f == 0);
+			const uint32_t inclusive = __ballot_sync(0xffffffffu, f == F_INCL);
+			const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+			const int first_in = inclusive ? __ffs(inclusive) - 1 : 32;
+			const int take = (first_in < first_nr) ? first_in + 1 : first_nr;
+			uint32_t c = ((int)lane < take) ? (v & ~F_MASK) : 0u;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				c += __shfl_xor_sync(0xffffffffu, c, o);
+			excl += c;
+			if (first_in < first_nr)
+				break;
+			p -= first_nr;
+		}
+		if (lane == 0) {
+			if (blk > 0) {
+				const uint32_t v = F_INCL | (excl + block_total);
+				asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.status + blk), "r"(v) : "memory");
+			}
+			s_bcast[1] = excl;
+			if (blk == gridDim.x - 1)
+				*a.count = excl + block_total;
+		}
+	}
+	__syncthreads();
+	if (visible)
+		a.indices[s_bcast[1] + warp_off + __popc(vmask & lanemask_lt())] = (long long)idx;
+}
+
 // ---- K11 ----------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
@@ -410,7 +490,10 @@ cudaError_t launch_filter(const FilterArgs& a, cudaStream_t stream)
 {
 	if (a.P <= 0)
 		return cudaSuccess;
-	filter_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
+	if (a.indices != nullptr)
+		filter_compact_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
+	else
+		filter_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
 }

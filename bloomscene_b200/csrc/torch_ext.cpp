@@ -407,12 +407,15 @@ torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, tor
 	return present;
 }
 
-torch::Tensor RasterizeGaussiansfilterCUDA(const torch::Tensor& means3D, const torch::Tensor& scales,
-                                           const torch::Tensor& rotations, const float scale_modifier,
-                                           const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
-                                           const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
-                                           const int image_height, const int image_width, const bool prefiltered,
-                                           const bool debug)
+namespace {
+// radii, and with `compact` also (indices int64 [P] capacity, count int32 [1]) of the Gaussians with radii > 0
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> filter_impl(const torch::Tensor& means3D, const torch::Tensor& scales,
+                                                                    const torch::Tensor& rotations, const float scale_modifier,
+                                                                    const torch::Tensor& cov3D_precomp,
+                                                                    const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+                                                                    const float tan_fovx, const float tan_fovy,
+                                                                    const int image_height, const int image_width,
+                                                                    const bool prefiltered, const bool debug, const bool compact)
 {
 	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
 		AT_ERROR("means3D must have dimensions (num_points, 3)");
@@ -421,6 +424,11 @@ torch::Tensor RasterizeGaussiansfilterCUDA(const torch::Tensor& means3D, const t
 	c10::cuda::CUDAGuard guard(means3D.device());
 	const int P = means3D.size(0);
 	torch::Tensor radii = torch::empty({P}, means3D.options().dtype(torch::kInt32));
+	torch::Tensor indices, count;
+	if (compact) {
+		indices = torch::empty({P}, means3D.options().dtype(torch::kInt64));
+		count = torch::zeros({1}, means3D.options().dtype(torch::kInt32));
+	}
 	if (P != 0) {
 		torch::Tensor k[6];
 		brs_view view{};
@@ -448,12 +456,43 @@ torch::Tensor RasterizeGaussiansfilterCUDA(const torch::Tensor& means3D, const t
 				scales_ptr = k[2].data_ptr<float>();
 			}
 		}
-		int st = brs_visible_filter(&view, P, req_ptr(means3D, k[3], "means3D"), scales_ptr, scales_stride,
-		                            opt_ptr(rotations, k[4], "rotations"), opt_ptr(cov3D_precomp, k[5], "cov3D_precomp"),
-		                            radii.data_ptr<int>(), current_stream());
+		int st;
+		if (compact) {
+			torch::Tensor scratch = torch::empty({(int64_t)brs_filter_scratch_bytes(P)}, means3D.options().dtype(torch::kByte));
+			st = brs_visible_filter_compact(&view, P, req_ptr(means3D, k[3], "means3D"), scales_ptr, scales_stride,
+			                                opt_ptr(rotations, k[4], "rotations"), opt_ptr(cov3D_precomp, k[5], "cov3D_precomp"),
+			                                radii.data_ptr<int>(), reinterpret_cast<long long*>(indices.data_ptr<int64_t>()),
+			                                reinterpret_cast<uint32_t*>(count.data_ptr<int>()), scratch.data_ptr(), current_stream());
+		} else {
+			st = brs_visible_filter(&view, P, req_ptr(means3D, k[3], "means3D"), scales_ptr, scales_stride,
+			                        opt_ptr(rotations, k[4], "rotations"), opt_ptr(cov3D_precomp, k[5], "cov3D_precomp"),
+			                        radii.data_ptr<int>(), current_stream());
+		}
 		check_status(st, "rasterize_aussians_filter");
 	}
-	return radii;
+	return std::make_tuple(radii, indices, count);
+}
+} // namespace
+
+torch::Tensor RasterizeGaussiansfilterCUDA(const torch::Tensor& means3D, const torch::Tensor& scales,
+                                           const torch::Tensor& rotations, const float scale_modifier,
+                                           const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                           const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                                           const int image_height, const int image_width, const bool prefiltered,
+                                           const bool debug)
+{
+	return std::get<0>(filter_impl(means3D, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+	                               tan_fovy, image_height, image_width, prefiltered, debug, false));
+}
+
+// Extension: (radii, indices int64 [P] of which the first count[0] are valid, count int32 [1])
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> RasterizeGaussiansfilterCompactCUDA(
+    const torch::Tensor& means3D, const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+    const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+    const float tan_fovy, const int image_height, const int image_width, const bool prefiltered, const bool debug)
+{
+	return filter_impl(means3D, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+	                   image_height, image_width, prefiltered, debug, true);
 }
 
 // ---- the steps either side of the rasterizer -----------------------------------------
@@ -703,6 +742,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("rasterize_gaussians_backward_depth", &RasterizeGaussiansBackwardDepthCUDA,
 	      pybind11::call_guard<pybind11::gil_scoped_release>());
 	m.def("rasterize_aussians_filter", &RasterizeGaussiansfilterCUDA);
+	m.def("rasterize_gaussians_filter_compact", &RasterizeGaussiansfilterCompactCUDA);
 	m.def("mark_visible", &markVisible);
 	m.def("sort_pairs", &SortPairs, pybind11::arg("keys"), pybind11::arg("vals") = pybind11::none(),
 	      pybind11::arg("begin_bit") = 0, pybind11::arg("end_bit") = 32);

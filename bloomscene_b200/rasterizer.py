@@ -225,6 +225,20 @@ def bind(_C) -> SimpleNamespace:
                                                     opt(cov3D_precomp), rs.viewmatrix, rs.projmatrix, rs.tanfovx,
                                                     rs.tanfovy, rs.image_height, rs.image_width, rs.prefiltered, rs.debug)
 
+        def visible_filter_indices(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
+            """Extension: `visible_filter` fused with the compaction BloomScene does next.  Returns
+            (radii int32 [P], visible_idx int64 [V]): visible_idx lists, ascending, the Gaussians with radii > 0 —
+            what `torch.nonzero(radii > 0)` would give — written by the same kernel, so the caller gathers its
+            per-anchor tensors with `t[visible_idx]` (index_select) instead of one boolean-mask nonzero each
+            (reference gaussian_renderer/__init__.py:39-60 indexes five tensors with visible_mask)."""
+            rs = self.raster_settings
+            opt = lambda t: _absent() if t is None else t
+            with torch.no_grad():
+                radii, idx, count = _C.rasterize_gaussians_filter_compact(
+                    means3D, opt(scales), opt(rotations), rs.scale_modifier, opt(cov3D_precomp), rs.viewmatrix, rs.projmatrix,
+                    rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, rs.prefiltered, rs.debug)
+                return radii, idx[: int(count.item())]
+
     def render_views(raster_settings_list, means3D, opacities, shs=None, colors_precomp=None, scales=None,
                      rotations=None, cov3D_precomp=None, streams=4, keep_radii=False, host_threads=True):
         """Forward-only render of one Gaussian set from a list of cameras (BloomScene's render_video loop,

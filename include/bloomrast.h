@@ -197,6 +197,17 @@ int brs_visible_filter(const brs_view* view, int P, const float* means3D,
                        const float* scales, int scales_stride, const float* rotations,
                        const float* cov3D_precomp, int* radii, brs_stream stream);
 
+/* Extension: the same filter fused with the compaction BloomScene performs next — it turns the
+ * radii into visible_mask = radii > 0 and boolean-indexes every per-anchor tensor with it
+ * (gaussian_renderer/__init__.py:294-349, :39-60).  Also writes `indices` (int64 [P] capacity): the ascending
+ * indices of the Gaussians with radii > 0, and their number into the device scalar `count`, in the same kernel.
+ * `scratch` = brs_filter_scratch_bytes(P) bytes. */
+size_t brs_filter_scratch_bytes(int P);
+int brs_visible_filter_compact(const brs_view* view, int P, const float* means3D,
+                               const float* scales, int scales_stride, const float* rotations,
+                               const float* cov3D_precomp, int* radii, long long* indices, uint32_t* count,
+                               void* scratch, brs_stream stream);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-30, rasterizer_impl.cu:141-153):
  * present[i] = (view-space z of mean i) > 0.2. */
 int brs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -17,6 +17,6 @@ def pytest_configure(config):
 def golden_files():
     import glob
 
-    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")) if not os.path.basename(f).startswith("loss_"))
     assert files, "tests/golden/*.npz missing"
     return files

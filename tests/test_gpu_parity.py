@@ -218,6 +218,14 @@ def test_visible_filter_and_mark_visible():
     assert r_mine.dtype == torch.int32 and torch.equal(r_mine, r_ref)
     fw = mine._C.rasterize_gaussians(*pl.forward_args(scene, cam, torch.zeros(3, device=DEV)))
     assert torch.equal(fw[3], r_mine)
+    # fused filter + compaction: same radii, and the index list torch.nonzero would give
+    r2, idx = mine.GaussianRasterizer(st).visible_filter_indices(scene.means3D, sliced, scene.rotations)
+    assert torch.equal(r2, r_ref) and idx.dtype == torch.int64
+    assert torch.equal(idx, torch.nonzero(r_ref > 0).flatten()) and idx.numel() > 1000
+    empty = synthetic.make_scene(700, "object", "precomp", -3.0, seed=1)
+    empty.means3D[:, 2] -= 10.0
+    r3, idx3 = mine.GaussianRasterizer(st).visible_filter_indices(empty.means3D.to(DEV), empty.scales.to(DEV), empty.rotations.to(DEV))
+    assert idx3.numel() == 0 and not r3.any()
     v_mine = mine.GaussianRasterizer(st).markVisible(scene.means3D)
     v_ref = ref.GaussianRasterizer(st).markVisible(scene.means3D)
     assert v_mine.dtype == torch.bool and torch.equal(v_mine, v_ref)

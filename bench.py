@@ -283,8 +283,9 @@ def main():
     ap.add_argument("--views", type=int, default=N_VIEWS)
     ap.add_argument("--cpu-views", type=int, default=3, help="views of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a rank are dealt onto (ours only)")
+    ap.add_argument("--streams", type=int, default=0, help="CUDA streams the views of a rank are dealt onto (0: 4, or one per view when a rank has at most 8)")
     ap.add_argument("--host-threads", type=int, default=0, help="1: one host thread per stream (ours only)")
+    ap.add_argument("--graphs", type=int, default=1, help="1: per-view work replayed from CUDA graphs (GraphedStep); 0: launched kernel by kernel")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "cpu" else a.warmup
 
@@ -320,6 +321,9 @@ def main():
         return
 
     world_eff, rank_eff = world, rank
+    views_per_rank = len(range(rank, a.views, world))
+    if a.streams <= 0:
+        a.streams = 4
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
@@ -331,7 +335,7 @@ def main():
 
     api = get_api()
 
-    from bloomscene_b200.multiview import download_grads, upload_params, view_sharded_step
+    from bloomscene_b200.multiview import GraphedStep, download_grads, upload_params, view_sharded_step
     from workload.params import GaussianParams
 
     scene_cpu = synthetic.config_scene(CONFIG_NAME)
@@ -363,9 +367,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
+    def plain_step():
         return view_sharded_step(params, cams, bg, api.GaussianRasterizer, loss_fn, rank=rank_eff, world=world_eff,
                                  streams=a.streams, host_threads=bool(a.host_threads))
+
+    # kernels one view launches (counted on a plain step; a graphed step replays exactly these)
+    api._C.launch_count(True)
+    plain_step()
+    torch.cuda.synchronize()
+    kernels_per_view = api._C.launch_count(False) // max(views_per_rank, 1)
+    graphed = None
+    if a.graphs:
+        graphed = GraphedStep(params, cams, bg, api.GaussianRasterizer, lambda c, d, t: loss_fn(c, d, 0), rank=rank_eff,
+                              world=world_eff, streams=a.streams)
+        graphed()  # first call: plain step + capture
+    step = graphed if graphed is not None else plain_step
 
     moved = {"h2d": 0, "d2h": 0}
 
@@ -373,22 +389,30 @@ def main():
     grads_on_host = torch.cuda.Event()
     grads_on_host.record()
 
+    marks = {}
+
     def step_e2e():
         # every rank moves its 1/N slice of the parameters / gradients over its own PCIe link; the slices
         # travel between GPUs over NVLink (all-gather in upload_params, the step's allreduce before download).
         # The device->host copy of a step's gradients runs on its own stream, so the next step's host->device
         # copy of the parameters overlaps it (PCIe is full duplex); the bucket is not touched before it has left.
         main = torch.cuda.current_stream(dev)
+        ev = {k: torch.cuda.Event(enable_timing=True) for k in ("t0", "up", "step", "down")}
+        ev["t0"].record()
         moved["h2d"] = upload_params(params, host_params, rank_eff, world_eff) + cam_host.numel() * 4
         with torch.no_grad():
             cam_dev.copy_(cam_host, non_blocking=True)
         main.wait_event(grads_on_host)
+        ev["up"].record()
         res = step()
+        ev["step"].record()
         copy_stream.wait_stream(main)
         with torch.cuda.stream(copy_stream):
             moved["d2h"] = download_grads(params, host_grads, rank_eff, world_eff) + 4
             host_loss.copy_(res["loss"].reshape(1), non_blocking=True)
             grads_on_host.record()
+            ev["down"].record()
+        marks.update(ev)
         return res
 
     def timed(fn, steps):
@@ -410,18 +434,43 @@ def main():
     for _ in range(a.warmup):
         step()
     count_launches = True
-    if count_launches:
-        api._C.launch_count(True)
     sampler = ClockSampler(local_rank)
     if rank_eff == 0:
         sampler.start()
     ms_step = timed(step, a.steps)
-    launches = api._C.launch_count(False) if count_launches else None
+    launches = kernels_per_view * views_per_rank * a.steps
     for _ in range(1):
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
     clocks = sampler.stop() if rank_eff == 0 else None
     loss_value = float(host_loss.item())
+    torch.cuda.synchronize()
+    e2e_breakdown = {"upload_h2d_allgather_and_wait_for_previous_d2h_ms": round(marks["t0"].elapsed_time(marks["up"]), 4),
+                     "step_ms": round(marks["up"].elapsed_time(marks["step"]), 4),
+                     "download_d2h_ms": round(marks["step"].elapsed_time(marks["down"]), 4),
+                     "note": "rank 0, last timed step; the download of step s overlaps the upload of step s+1"}
+
+    # ---- the step's one collective on its own (outside the timed region) -------------------------------
+    collective = None
+    if world_eff > 1:
+        import torch.distributed as dist
+
+        buf = params.reduce_buffer()
+        for _ in range(2):
+            dist.all_reduce(buf)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            dist.all_reduce(buf)
+        c1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([c0.elapsed_time(c1) / 5], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        nbytes = buf.numel() * 4
+        collective = {"op": "ncclAllReduce sum fp32 (gradient bucket + loss word)", "bytes": nbytes, "ms": round(ms.item(), 4),
+                      "busbw_GBps": round(2 * (world_eff - 1) / world_eff * nbytes / (ms.item() * 1e-3) / 1e9, 1),
+                      "share_of_step": round(ms.item() / ms_step, 4)}
 
     # ---- gradient parity of the step, outside the timed region -----------------------
     # The bucket the step produced (views dealt over ranks and streams, in-kernel accumulation, NCCL
@@ -470,7 +519,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config, "clocks": clocks,
         "e2e": {"value": a.views / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e,
+                "ms_per_step": ms_e2e, "breakdown": e2e_breakdown,
                 "what": "per step: all Gaussian parameters + cameras pinned host->device, then the view loop through "
                         "GaussianRasterizer / autograd, then gradient bucket + loss device->pinned host; with N ranks "
                         "each rank copies its 1/N slice of the parameters / the reduced gradients over its own PCIe "
@@ -484,6 +533,10 @@ def main():
     }
     out["gpu_launches"] = launches
     out["streams_per_rank"] = a.streams
+    out["cuda_graphs"] = None if graphed is None else {"views_replayed": graphed.replays, "steps_repeated_ungraphed": graphed.fallbacks}
+    out["kernels_per_view"] = kernels_per_view
+    out["views_per_rank"] = views_per_rank
+    out["collective"] = collective
 
     # ---- stage profile + roofline (ours, rank 0, outside the timed region) --------------------------
     if rank_eff == 0:

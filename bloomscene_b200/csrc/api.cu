@@ -501,7 +501,8 @@ struct ForwardCtx {
 // Everything after preprocess, sized by `caps`: depth sort -> emission -> coarse sort -> fine binning ->
 // blend.  No host wait in here.  If `report` is given, the header (counts + overflow word) is copied to
 // it right after the depth sort's histogram kernel has judged the capacities.
-int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* report, cudaEvent_t report_event)
+int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* report, cudaEvent_t report_event,
+                              uint32_t* overflow_accum = nullptr)
 {
 	cudaStream_t stream = c.stream;
 	const bool debug = c.debug;
@@ -527,6 +528,7 @@ int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* r
 	pl.order = reinterpret_cast<uint32_t*>(c.geom + c.gl.order);
 	pl.point_list = reinterpret_cast<uint32_t*>(binning);
 	pl.ranges = reinterpret_cast<uint2*>(c.image + c.il.ranges);
+	pl.overflow_accum = overflow_accum;
 
 	const bool have_grid = c.grid_x * c.grid_y > 0;
 	if (have_grid) {
@@ -607,7 +609,7 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 	const int mode = opt ? opt->mode : BRS_FWD_AUTO;
 	if (mode != BRS_FWD_AUTO && mode != BRS_FWD_EXACT && mode != BRS_FWD_DEFERRED)
 		return BRS_ERR_INVALID_ARG;
-	if (mode == BRS_FWD_DEFERRED && opt->report == nullptr)
+	if (mode == BRS_FWD_DEFERRED && opt->report == nullptr && opt->overflow_accum == nullptr)
 		return BRS_ERR_INVALID_ARG;
 	const int W = view->image_width, H = view->image_height, P = g->P;
 	const size_t npix = (size_t)W * H;
@@ -624,7 +626,7 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 			BRS_CUDA(cudaMemsetAsync(out_color, 0, sizeof(float) * NUM_CHANNELS * npix, stream));
 			BRS_CUDA(cudaMemsetAsync(out_depth, 0, sizeof(float) * npix, stream));
 		}
-		if (mode == BRS_FWD_DEFERRED)
+		if (mode == BRS_FWD_DEFERRED && opt->report != nullptr)
 			memset(opt->report, 0, HDR_WORDS * sizeof(uint32_t));
 		return BRS_OK;
 	}
@@ -709,7 +711,7 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 			return BRS_ERR_UNSUPPORTED;
 		state->num_rendered = -1; // on the device; the caller reads it from `report` once the stream has passed it
 		t_fwd_stats[3]++;
-		return enqueue_binning_and_blend(c, caps, opt->report, nullptr);
+		return enqueue_binning_and_blend(c, caps, opt->report, nullptr, opt->overflow_accum);
 	}
 
 	BRS_CUDA(ensure_slot());

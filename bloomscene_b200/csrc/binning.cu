@@ -119,6 +119,7 @@ struct HistArgs {
 	int shift[4], bits[4];
 	int drop;                // keys equal to DEPTH_KEY_CULLED do not take part
 	uint32_t R_cap, R1_cap;  // for the overflow word (depth sort only)
+	uint32_t* overflow_accum; // optional: the overflow bits are also OR-ed into this word
 	uint32_t* hist;          // [passes][RADIX], pre-zeroed
 };
 
@@ -152,6 +153,8 @@ __global__ void __launch_bounds__(OS_THREADS) radix_hist_kernel(HistArgs a)
 			flags |= 4u;
 		a.hdr_out[HDR_OVERFLOW] = flags;
 		a.hdr_out[HDR_KEY_BITS] = nbits;
+		if (a.overflow_accum != nullptr && flags != 0u)
+			atomicOr(a.overflow_accum, flags);
 	}
 	for (uint32_t i = blockIdx.x * OS_THREADS + tid; i < n; i += gridDim.x * OS_THREADS) {
 		const uint32_t key = __ldg(a.keys + i);
@@ -859,6 +862,7 @@ cudaError_t launch_depth_sort_begin(const BinPlan& pl, int planned_passes, cudaS
 	h.drop = 1;
 	h.R_cap = pl.R_cap;
 	h.R1_cap = pl.R1_cap;
+	h.overflow_accum = pl.overflow_accum;
 	h.hist = pl.d.hist;
 	const uint32_t hist_grid = (uint32_t)std::min<size_t>((pl.P + 2047) / 2048, 296);
 	radix_hist_kernel<<<hist_grid, OS_THREADS, 0, stream>>>(h);

@@ -121,6 +121,7 @@ struct BinPlan {
 	uint32_t grid_x, grid_y, ns_x, ns;
 	int depth_passes;          // 8-bit digits of (depth key - bias) that are sorted on
 	uint32_t* hdr;             // geometry header
+	uint32_t* overflow_accum;  // optional device word that collects the overflow bits of many forwards (atomicOr)
 	const uint32_t* depth_key; // [P]
 	const uint2* rect;         // [P]
 	uint32_t* order;           // [P]: the V visible ids in (depth bits, id) order

@@ -93,7 +93,8 @@ ForwardTuple RasterizeGaussiansExCUDA(const torch::Tensor& background, const tor
                                       const float tan_fovy, const int image_height, const int image_width,
                                       const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
                                       const bool prefiltered, const bool debug, const int mode, const int R_cap,
-                                      const int R1_cap, const int depth_bits, const c10::optional<torch::Tensor>& report)
+                                      const int R1_cap, const int depth_bits, const c10::optional<torch::Tensor>& report,
+                                      const c10::optional<torch::Tensor>& overflow_accum)
 {
 	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
 		AT_ERROR("means3D must have dimensions (num_points, 3)");
@@ -154,6 +155,11 @@ ForwardTuple RasterizeGaussiansExCUDA(const torch::Tensor& background, const tor
 		            "report must be a pinned contiguous CPU int32 tensor of at least 8 elements");
 		opt.report = reinterpret_cast<uint32_t*>(report->data_ptr<int>());
 	}
+	if (overflow_accum.has_value() && overflow_accum->defined()) {
+		TORCH_CHECK(overflow_accum->is_cuda() && overflow_accum->scalar_type() == torch::kInt32 && overflow_accum->numel() >= 1,
+		            "overflow_accum must be a CUDA int32 tensor");
+		opt.overflow_accum = reinterpret_cast<uint32_t*>(overflow_accum->data_ptr<int>());
+	}
 	brs_fwd_state state{};
 	int st = brs_forward_ex(&view, &g, out_color.data_ptr<float>(), out_depth.data_ptr<float>(),
 	                        P ? radii.data_ptr<int>() : nullptr, alloc_cb, &ctx, &state, &opt, current_stream());
@@ -172,7 +178,7 @@ ForwardTuple RasterizeGaussiansCUDA(const torch::Tensor& background, const torch
 {
 	return RasterizeGaussiansExCUDA(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
 	                                viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-	                                prefiltered, debug, BRS_FWD_AUTO, 0, 0, 0, c10::nullopt);
+	                                prefiltered, debug, BRS_FWD_AUTO, 0, 0, 0, c10::nullopt, c10::nullopt);
 }
 
 namespace {
@@ -716,7 +722,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	// the forward blocks once on the device (instance count); it touches no Python object, so it runs
 	// without the GIL and several host threads can drive one CUDA stream each (render_views)
 	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
-	m.def("rasterize_gaussians_ex", &RasterizeGaussiansExCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
+	m.def("rasterize_gaussians_ex", &RasterizeGaussiansExCUDA, pybind11::arg("bg"), pybind11::arg("means3D"), pybind11::arg("colors"),
+	      pybind11::arg("opacity"), pybind11::arg("scales"), pybind11::arg("rotations"), pybind11::arg("scale_modifier"),
+	      pybind11::arg("cov3D_precomp"), pybind11::arg("viewmatrix"), pybind11::arg("projmatrix"), pybind11::arg("tan_fovx"),
+	      pybind11::arg("tan_fovy"), pybind11::arg("image_height"), pybind11::arg("image_width"), pybind11::arg("sh"),
+	      pybind11::arg("degree"), pybind11::arg("campos"), pybind11::arg("prefiltered"), pybind11::arg("debug"),
+	      pybind11::arg("mode"), pybind11::arg("R_cap") = 0, pybind11::arg("R1_cap") = 0, pybind11::arg("depth_bits") = 0,
+	      pybind11::arg("report") = pybind11::none(), pybind11::arg("overflow_accum") = pybind11::none(),
+	      pybind11::call_guard<pybind11::gil_scoped_release>());
 	m.def("note_counts", [](int P, int W, int H, const torch::Tensor& report) {
 		TORCH_CHECK(report.is_cpu() && report.scalar_type() == torch::kInt32 && report.numel() >= 8 && report.is_contiguous());
 		brs_note_counts(P, W, H, reinterpret_cast<const uint32_t*>(report.data_ptr<int>()));

@@ -94,15 +94,18 @@ def bind(_C) -> SimpleNamespace:
 
         @staticmethod
         def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                    raster_settings, grad_sink=None, depth_gradient=False):
+                    raster_settings, grad_sink=None, depth_gradient=False, deferred_overflow=None):
             rs = raster_settings
-            out = _guarded(
-                _C.rasterize_gaussians,
-                (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
-                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
-                 rs.sh_degree, rs.campos, rs.prefiltered, rs.debug),
-                rs.debug, "snapshot_fw.dump",
-                "\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+            args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                    rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
+                    rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+            if deferred_overflow is not None:
+                # extension: no host wait at all (brs_fwd_options DEFERRED); capacity overflows are OR-ed into the
+                # caller's device word, which it checks once per batch of views (a CUDA graph can hold this call)
+                out = _C.rasterize_gaussians_ex(*args, _C.FWD_DEFERRED, 0, 0, 0, None, deferred_overflow)
+            else:
+                out = _guarded(_C.rasterize_gaussians, args, rs.debug, "snapshot_fw.dump",
+                               "\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
             num_rendered, color, depth, radii, geom, binning, image = out
             ctx.raster_settings = rs
             ctx.grad_sink = grad_sink
@@ -132,7 +135,7 @@ def bind(_C) -> SimpleNamespace:
                      k.get("scales"), k.get("rotations"), out_depth),
                     rs.debug, "snapshot_bw.dump",
                     "\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
-                return None, d_means2D, None, None, None, None, None, None, None, None, None
+                return None, d_means2D, None, None, None, None, None, None, None, None, None, None
             if ctx.depth_gradient:
                 # extension: grad_depth is back-propagated through the depth image (default off = reference)
                 g = _guarded(
@@ -143,7 +146,7 @@ def bind(_C) -> SimpleNamespace:
                     rs.debug, "snapshot_bw.dump",
                     "\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 d_means2D, d_colors, d_opacities, d_means3D, d_cov3D, d_sh, d_scales, d_rotations = g
-                return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None, None
+                return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None, None, None
             g = _guarded(
                 _C.rasterize_gaussians_backward,
                 (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
@@ -154,16 +157,20 @@ def bind(_C) -> SimpleNamespace:
             d_means2D, d_colors, d_opacities, d_means3D, d_cov3D, d_sh, d_scales, d_rotations = g
             # one gradient per autograd input, in input order (reference __init__.py:144-154);
             # grad_radii carries nothing and grad_depth is plumbed down but unused by the kernels
-            return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None, None
+            return d_means3D, d_means2D, d_sh, d_colors, d_opacities, d_scales, d_rotations, d_cov3D, None, None, None, None
 
     has_sink = hasattr(_C, "rasterize_gaussians_backward_accumulate")
     has_depth_grad = hasattr(_C, "rasterize_gaussians_backward_depth")
 
+    has_deferred = hasattr(_C, "rasterize_gaussians_ex")
+
     def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                            raster_settings, grad_sink=None, depth_gradient=False):
+                            raster_settings, grad_sink=None, depth_gradient=False, deferred_overflow=None):
         # reference __init__.py:21-42; `grad_sink` and `depth_gradient` are extensions (see GaussianRasterizer)
         if depth_gradient and not has_depth_grad:
             raise Exception('this native module has no depth gradient (the reference comments it out)')
+        if deferred_overflow is not None and not has_deferred:
+            raise Exception('this native module has no deferred forward')
         if grad_sink is not None:
             if not has_sink:
                 raise Exception('this native module has no in-place gradient accumulation (grad_sink)')
@@ -173,7 +180,7 @@ def bind(_C) -> SimpleNamespace:
                 if t.numel() != 0 and t.requires_grad and name not in grad_sink:
                     raise Exception(f'grad_sink has no entry for {name}, whose gradient would be dropped')
         return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                         cov3Ds_precomp, raster_settings, grad_sink, depth_gradient)
+                                         cov3Ds_precomp, raster_settings, grad_sink, depth_gradient, deferred_overflow)
 
     class GaussianRasterizer(nn.Module):
         """reference __init__.py:172-249: forward / visible_filter / markVisible with the same signatures.
@@ -192,12 +199,17 @@ def bind(_C) -> SimpleNamespace:
 
         supports_grad_sink = has_sink
         supports_depth_gradient = has_depth_grad
+        supports_deferred = has_deferred
 
-        def __init__(self, raster_settings, grad_sink=None, depth_gradient=False):
+        def __init__(self, raster_settings, grad_sink=None, depth_gradient=False, deferred_overflow=None):
             super().__init__()
             self.raster_settings = raster_settings
             self.grad_sink = grad_sink
             self.depth_gradient = depth_gradient
+            # Extension: a CUDA int32[1] tensor switches the forward to brs_fwd_options DEFERRED - no host
+            # synchronisation in forward or backward, buffers sized from the high-water marks of the shape, capacity
+            # overflows OR-ed into the tensor (non-zero = this forward's results are invalid, run it again without).
+            self.deferred_overflow = deferred_overflow
 
         def markVisible(self, positions):
             rs = self.raster_settings
@@ -215,7 +227,7 @@ def bind(_C) -> SimpleNamespace:
             opt = lambda t: _absent() if t is None else t
             return rasterize_gaussians(means3D, means2D, opt(shs), opt(colors_precomp), opacities, opt(scales),
                                        opt(rotations), opt(cov3D_precomp), self.raster_settings, self.grad_sink,
-                                       self.depth_gradient)
+                                       self.depth_gradient, self.deferred_overflow)
 
         def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
             rs = self.raster_settings

@@ -163,7 +163,10 @@ typedef struct brs_fwd_options {
 	int R_cap;        /* DEFERRED: capacity of the binning buffer in tile instances (0: high-water mark) */
 	int R1_cap;       /* DEFERRED: capacity in supertile instances (0: high-water mark) */
 	int depth_bits;   /* DEFERRED: significant depth-key bits to sort on (0: high-water mark) */
-	uint32_t* report; /* DEFERRED: 8 words of pinned host memory */
+	uint32_t* report; /* DEFERRED: 8 words of pinned host memory (may be NULL when overflow_accum is given) */
+	/* DEFERRED, optional: DEVICE word into which the overflow bits of this forward are OR-ed.  A caller that
+	 * replays a captured forward many times (CUDA graph) zeroes it once, reads it once per batch. */
+	uint32_t* overflow_accum;
 } brs_fwd_options;
 int brs_forward_ex(const brs_view* view, const brs_gaussians* g,
                    float* out_color, float* out_depth, int* radii,

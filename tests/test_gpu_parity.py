@@ -618,3 +618,46 @@ def test_render_views_deferred_batch_recovers_from_overflow_and_replays_in_a_cud
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
         assert pl.rel_l2(got[2], want[2]) <= 1e-5 and pl.rel_l2(got[3], want[3]) <= 1e-5
     _C.reset_marks()
+
+
+def test_graphed_step_matches_the_plain_step_and_survives_an_overflow():
+    """GraphedStep: per-view forward + loss + backward replayed from CUDA graphs must give the
+    plain step's gradients; when the captured capacities become too small the step is repeated un-graphed."""
+    from bloomscene_b200.multiview import GraphedStep, view_sharded_step
+    from workload.params import GaussianParams
+
+    api = pl.ours()
+    _C = api._C
+    _C.reset_marks()
+    scene = synthetic.make_scene(8000, "object", "sh3", -3.8, seed=17).to(DEV)
+    W, H = 208, 144
+    cams = [synthetic.orbit_camera(W, H, 0.7 * k).to(DEV) for k in range(7)]
+    Wc, Wd = [t.to(DEV) for t in synthetic.loss_weights(W, H)]
+    targets = torch.rand(len(cams), 3, H, W, device=DEV)
+    bg = torch.tensor([0.2, 0.1, 0.4], device=DEV)
+    loss3 = lambda c, d, t: ((c - t) ** 2 * Wc).sum() + (d * Wd).sum()
+    got, want = GaussianParams(scene), GaussianParams(scene)
+    step = GraphedStep(got, cams, bg, api.GaussianRasterizer, loss3, streams=3, targets=targets)
+    step()  # plain + capture
+    for _ in range(2):
+        res = step()
+    assert step.replays == 2 * len(cams) and step.fallbacks == 0
+    ref = view_sharded_step(want, cams, bg, api.GaussianRasterizer, lambda c, d, vi: loss3(c, d, targets[vi]), streams=1)
+    assert float(res["loss"]) == pytest.approx(float(ref["loss"]), rel=1e-6)
+    for name in got.names:
+        assert float(want.tensors[name].grad.abs().max()) > 0, name
+        assert pl.rel_l2(got.tensors[name].grad, want.tensors[name].grad) <= pl.GRAD_TOL, name
+    # the Gaussians grow 3x: the captured capacities overflow -> the step is repeated un-graphed and re-captured
+    with torch.no_grad():
+        got.tensors["scales"].mul_(3.0)
+        want.tensors["scales"].mul_(3.0)
+    res = step()
+    assert step.fallbacks == 1
+    ref = view_sharded_step(want, cams, bg, api.GaussianRasterizer, lambda c, d, vi: loss3(c, d, targets[vi]), streams=1)
+    for name in got.names:
+        assert pl.rel_l2(got.tensors[name].grad, want.tensors[name].grad) <= pl.GRAD_TOL, name
+    res = step()  # graphs again, with the larger capacities
+    assert step.fallbacks == 1
+    for name in got.names:
+        assert pl.rel_l2(got.tensors[name].grad, want.tensors[name].grad) <= pl.GRAD_TOL, name
+    _C.reset_marks()

@@ -27,7 +27,12 @@ class GaussianParams:
         dev = scene.means3D.device
         sizes = [tensors[n].numel() for n in self.names]
         self.flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        self.grad_bucket = torch.zeros_like(self.flat)
+        # two extra words behind the gradients carry the step loss and a "some rank must repeat this step" count,
+        # so that a multi-rank step needs ONE collective
+        self._bucket_ext = torch.zeros(sum(sizes) + 2, dtype=torch.float32, device=dev)
+        self.grad_bucket = self._bucket_ext[:sum(sizes)]
+        self.loss_slot = self._bucket_ext[sum(sizes):sum(sizes) + 1]
+        self.flag_slot = self._bucket_ext[sum(sizes) + 1:]
         self.tensors: Dict[str, torch.Tensor] = {}
         self._zero_means2D = None
         off = 0
@@ -44,7 +49,11 @@ class GaussianParams:
         return self.tensors["means3D"].shape[0]
 
     def zero_grad(self):
-        self.grad_bucket.zero_()
+        self._bucket_ext.zero_()
+
+    def reduce_buffer(self) -> torch.Tensor:
+        """What a multi-rank step all-reduces: the gradient bucket followed by the loss and the repeat-flag words."""
+        return self._bucket_ext
 
     def zero_means2D(self) -> torch.Tensor:
         """The all-zero `means2D` input every view passes in (reference gaussian_renderer/__init__.py:224-229

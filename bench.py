@@ -91,6 +91,29 @@ class ClockSampler:
 
 # ---- helpers -------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(index: int):
+    """Best effort: run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
+    allocated (first touch then places the staging buffers of the end-to-end leg next to the GPU's PCIe root)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus  # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA node for this GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return {"numa_node": node, "note": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # pragma: no cover
+        return {"numa_node": None, "note": str(e)[:120]}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -285,7 +308,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=0, help="CUDA streams the views of a rank are dealt onto (0: 4, or one per view when a rank has at most 8)")
     ap.add_argument("--host-threads", type=int, default=0, help="1: one host thread per stream (ours only)")
-    ap.add_argument("--graphs", type=int, default=1, help="1: per-view work replayed from CUDA graphs (GraphedStep); 0: launched kernel by kernel")
+    ap.add_argument("--graphs", type=int, default=-1, help="1: per-view work replayed from CUDA graphs (GraphedStep); 0: launched kernel by kernel; "
+                    "-1: graphs when a rank has at most 16 views (the host's launch rate matters when a step is short)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "cpu" else a.warmup
 
@@ -326,6 +350,7 @@ def main():
         a.streams = 4
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world_eff > 1:
@@ -377,6 +402,8 @@ def main():
     torch.cuda.synchronize()
     kernels_per_view = api._C.launch_count(False) // max(views_per_rank, 1)
     graphed = None
+    if a.graphs < 0:
+        a.graphs = 1 if views_per_rank <= 16 else 0
     if a.graphs:
         graphed = GraphedStep(params, cams, bg, api.GaussianRasterizer, lambda c, d, t: loss_fn(c, d, 0), rank=rank_eff,
                               world=world_eff, streams=a.streams)
@@ -537,6 +564,7 @@ def main():
     out["kernels_per_view"] = kernels_per_view
     out["views_per_rank"] = views_per_rank
     out["collective"] = collective
+    out["numa_binding"] = numa
 
     # ---- stage profile + roofline (ours, rank 0, outside the timed region) --------------------------
     if rank_eff == 0:

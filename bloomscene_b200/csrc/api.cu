@@ -13,7 +13,9 @@
 // brs_backward: memset(accumulator) -> blend backward -> fused preprocess backward (plain or
 // accumulate mode, see brs_grads).  No host sync.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -100,12 +102,21 @@ struct StageTimer {
 };
 thread_local StageTimer t_timer;
 
+int g_nvtx_enabled = 0;
+const char* const kStageNames[BRS_NUM_STAGES] = {"brs:preprocess", "brs:depth_sort", "brs:coarse_emit", "brs:coarse_sort",
+                                                 "brs:fine_bin", "brs:blend_fwd", "brs:blend_bwd", "brs:preprocess_bwd"};
+
 struct StageScope {
 	int stage;
 	cudaStream_t stream;
 	cudaEvent_t a = nullptr;
+	bool nvtx = false;
 	StageScope(int stage_, cudaStream_t s) : stage(stage_), stream(s)
 	{
+		if (g_nvtx_enabled && stage >= 0 && stage < BRS_NUM_STAGES) {
+			nvtxRangePushA(kStageNames[stage]); // host-side range around the stage's launches (nsys / ncu --nvtx)
+			nvtx = true;
+		}
 		if (t_timer.enabled) {
 			a = t_timer.get();
 			cudaEventRecord(a, stream);
@@ -113,6 +124,8 @@ struct StageScope {
 	}
 	~StageScope()
 	{
+		if (nvtx)
+			nvtxRangePop();
 		if (a != nullptr) {
 			cudaEvent_t b = t_timer.get();
 			cudaEventRecord(b, stream);
@@ -353,6 +366,14 @@ int brs_state_layout(int P, int R, int W, int H, brs_layout* out)
 }
 
 void brs_stage_timing(int enable) { t_timer.enabled = enable != 0; }
+
+int brs_stage_nvtx(int enable)
+{
+	const int old = g_nvtx_enabled;
+	if (enable >= 0)
+		g_nvtx_enabled = enable != 0;
+	return old;
+}
 
 int brs_blend_companion_stream(int enable)
 {
@@ -606,6 +627,13 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 		return st;
 	if (alloc == nullptr || state == nullptr)
 		return BRS_ERR_INVALID_ARG;
+	static const bool nvtx_env = [] {
+		const char* e = getenv("BRS_NVTX");
+		if (e != nullptr && e[0] == '1')
+			g_nvtx_enabled = 1;
+		return true;
+	}();
+	(void)nvtx_env;
 	const int mode = opt ? opt->mode : BRS_FWD_AUTO;
 	if (mode != BRS_FWD_AUTO && mode != BRS_FWD_EXACT && mode != BRS_FWD_DEFERRED)
 		return BRS_ERR_INVALID_ARG;

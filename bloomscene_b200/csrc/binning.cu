@@ -654,23 +654,24 @@ __global__ void __launch_bounds__(FINE_WARPS * 32)
 	}
 }
 
-// Per supertile (one CTA, 4 groups x 64 tiles): exclusive prefix of the slice counts along the
+// Per supertile (one CTA, FS_GROUPS groups x 64 tiles): exclusive prefix of the slice counts along the
 // slices, in place, and the per-tile totals into tile_count[tile id].  The last CTA to finish then
 // scans the per-tile totals in tile-id order -> tile_start, and the tile ranges (reference
 // identifyTileRanges: tiles without instances keep (0, 0)); ranges are clamped to the capacity of
 // `point_list` so that an overflowing forward stays memory-safe.
-__global__ void __launch_bounds__(256)
+constexpr int FS_GROUPS = 16; // a supertile's slices are cut into this many runs, one per 64-thread group
+__global__ void __launch_bounds__(FS_GROUPS * ST_TILES)
     fine_scan_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slice_base, uint32_t ns_x, uint32_t grid_x,
                      uint32_t grid_y, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_start,
                      uint2* __restrict__ ranges, uint32_t R_cap, uint32_t* done)
 {
-	__shared__ uint32_t s_part[4][ST_TILES];
+	__shared__ uint32_t s_part[FS_GROUPS][ST_TILES];
 	__shared__ uint32_t s_warp[OS_WARPS];
 	__shared__ uint32_t s_last;
 	const uint32_t st = blockIdx.x;
 	const uint32_t first = __ldg(slice_base + st), nsl = __ldg(slice_base + st + 1) - first;
 	const uint32_t t = threadIdx.x & 63, q = threadIdx.x >> 6;
-	const uint32_t per = (nsl + 3) / 4;
+	const uint32_t per = (nsl + FS_GROUPS - 1) / FS_GROUPS;
 	const uint32_t j0 = min(q * per, nsl), j1 = min(j0 + per, nsl);
 	uint32_t* col = table + (size_t)first * ST_TILES + t;
 	uint32_t sum = 0;
@@ -681,7 +682,7 @@ __global__ void __launch_bounds__(256)
 	__syncthreads();
 	uint32_t run = 0, total = 0;
 #pragma unroll
-	for (uint32_t k = 0; k < 4; k++) {
+	for (uint32_t k = 0; k < FS_GROUPS; k++) {
 		const uint32_t v = s_part[k][t];
 		if (k < q)
 			run += v;
@@ -703,10 +704,11 @@ __global__ void __launch_bounds__(256)
 	if (threadIdx.x == 0)
 		s_last = atomicAdd(done, 1u);
 	__syncthreads();
-	if (s_last != gridDim.x - 1)
+	if (s_last != gridDim.x - 1 || threadIdx.x >= 256)
 		return;
 	__threadfence();
-	// exclusive scan over all tiles in tile-id order: every thread takes a contiguous run of tiles
+	// exclusive scan over all tiles in tile-id order by the CTA's first 256 threads (named barrier 1: the other
+	// threads have left): every thread takes a contiguous run of tiles
 	const uint32_t num_tiles = grid_x * grid_y;
 	const uint32_t chunk = (num_tiles + 255) / 256;
 	const uint32_t t0 = min(threadIdx.x * chunk, num_tiles), t1 = min(t0 + chunk, num_tiles);
@@ -960,7 +962,7 @@ cudaError_t launch_fine_binning(const BinPlan& pl, cudaStream_t stream)
 		                                                            pl.ns_x, pl.grid_x, pl.grid_y, b.table, nullptr, nullptr, 0u);
 		count_launch();
 	}
-	fine_scan_kernel<<<pl.ns, 256, 0, stream>>>(b.table, b.slice_base, pl.ns_x, pl.grid_x, pl.grid_y, b.tile_count,
+	fine_scan_kernel<<<pl.ns, FS_GROUPS * ST_TILES, 0, stream>>>(b.table, b.slice_base, pl.ns_x, pl.grid_x, pl.grid_y, b.tile_count,
 	                                            b.tile_start, pl.ranges, pl.R_cap, b.ctl + ICTL_FINE_DONE);
 	count_launch();
 	if (pl.R1_cap > 0 && pl.R_cap > 0) {

@@ -718,6 +718,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("count_pairs", &CountPairs);
 	m.def("stage_timing", [](bool enable) { brs_stage_timing(enable ? 1 : 0); });
 	m.def("stage_times", &StageTimes);
+	m.def("stage_nvtx", [](int enable) { return brs_stage_nvtx(enable); }, pybind11::arg("enable") = -1);
 	m.def("probe_fp32_tflops", []() { return brs_probe_fp32_tflops(current_stream()); });
 	// the forward blocks once on the device (instance count); it touches no Python object, so it runs
 	// without the GIL and several host threads can drive one CUDA stream each (render_views)

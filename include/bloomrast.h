@@ -329,6 +329,10 @@ enum {
 };
 /* When enabled, every stage is bracketed by CUDA events on the call's stream (per thread). */
 void brs_stage_timing(int enable);
+/* When enabled (process-wide), the launches of every stage sit inside an NVTX range named "brs:<stage>", for
+ * nsys timelines and `ncu --nvtx --nvtx-include`.  enable: 1 / 0 to set, -1 to query; returns the previous setting.
+ * Also switched on by the environment variable BRS_NVTX=1 at the first forward. */
+int brs_stage_nvtx(int enable);
 
 /* Scheduling option (no reference counterpart).  When the caller's stream has a higher priority than
  * the device's lowest, brs_forward / brs_backward launch their blend kernels on an internal

@@ -37,7 +37,7 @@ launches)
     --log-file gpurun_out/${TAG}_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu1.log 2>&1
   tail -2 gpurun_out/${TAG}_ncu1.log ;;
 ncu)
-  timeout 1500 ncu --set full --clock-control none --import-source on -k "$K" --launch-skip ${NCU_SKIP:-20} --launch-count ${NCU_COUNT:-20} \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k "$K" --launch-skip ${NCU_SKIP:-13} --launch-count ${NCU_COUNT:-13} \
     -f -o gpurun_out/${TAG}_full python tests/profile_step.py --impl ours --config C --iters 2 > gpurun_out/${TAG}_ncu2.log 2>&1
   tail -2 gpurun_out/${TAG}_ncu2.log ;;
 esac

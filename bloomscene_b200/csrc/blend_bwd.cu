@@ -85,41 +85,43 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int
 		const float2 g = *reinterpret_cast<const float2*>(&rec[idx].geo);
 		const float4 con = rec[idx].con;
 		id = s_id[idx];
-		const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(srow + stage_row(q));
-		const ulonglong2* up = reinterpret_cast<const ulonglong2*>(srow + STAGE_U + stage_row(q));
-		f32x2 w[8], u[8];
-#pragma unroll
-		for (int k = 0; k < 4; k++) {
-			const ulonglong2 a = wp[k], b = up[k];
-			w[2 * k] = a.x; w[2 * k + 1] = a.y;
-			u[2 * k] = b.x; u[2 * k + 1] = b.y;
-		}
+		// phase 1: the moments of w along x (both rows packed); w's registers are dead before u is fetched
 		const float dyA = g.y - (byf + (float)q), dyB = g.y - (byf + (float)(q + 4));
 		const float dx0 = g.x - bxf;
 		f32x2 S0 = bc2(0.f), Sx = bc2(0.f), Sxx = bc2(0.f);
+		{
+			const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(srow + stage_row(q));
 #pragma unroll
-		for (int i = 0; i < 8; i++) {
-			const f32x2 dx = bc2(dx0 - (float)i);
-			const f32x2 t = mul2(w[i], dx);
-			S0 = add2(S0, w[i]);
-			Sx = add2(Sx, t);
-			Sxx = fma2(t, dx, Sxx);
+			for (int k = 0; k < 4; k++) {
+				const ulonglong2 a = wp[k];
+				const f32x2 dxa = bc2(dx0 - (float)(2 * k)), dxb = bc2(dx0 - (float)(2 * k + 1));
+				const f32x2 ta = mul2(a.x, dxa), tb = mul2(a.y, dxb);
+				S0 = add2(S0, add2(a.x, a.y));
+				Sx = add2(Sx, add2(ta, tb));
+				Sxx = fma2(ta, dxa, Sxx);
+				Sxx = fma2(tb, dxb, Sxx);
+			}
 		}
+		// phase 2: the colour sums of u
 		constexpr int NCH = DEPTH ? 4 : 3; // with DEPTH the 4th plane of s_dpx holds gD = dL_dD
 		float c[4] = {0.f, 0.f, 0.f, 0.f};
+		{
+			const ulonglong2* up = reinterpret_cast<const ulonglong2*>(srow + STAGE_U + stage_row(q));
+			const ulonglong2 u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
 #pragma unroll
-		for (int ch = 0; ch < NCH; ch++) {
-			const ulonglong2* dp = reinterpret_cast<const ulonglong2*>(s_dpx + ch * PLANE + q * ROW_PITCH);
-			const ulonglong2 d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3];
-			f32x2 s = mul2(u[0], d0.x);
-			s = fma2(u[1], d0.y, s);
-			s = fma2(u[2], d1.x, s);
-			s = fma2(u[3], d1.y, s);
-			s = fma2(u[4], d2.x, s);
-			s = fma2(u[5], d2.y, s);
-			s = fma2(u[6], d3.x, s);
-			s = fma2(u[7], d3.y, s);
-			c[ch] = lo2(s) + hi2(s);
+			for (int ch = 0; ch < NCH; ch++) {
+				const ulonglong2* dp = reinterpret_cast<const ulonglong2*>(s_dpx + ch * PLANE + q * ROW_PITCH);
+				const ulonglong2 d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3];
+				f32x2 s = mul2(u0.x, d0.x);
+				s = fma2(u0.y, d0.y, s);
+				s = fma2(u1.x, d1.x, s);
+				s = fma2(u1.y, d1.y, s);
+				s = fma2(u2.x, d2.x, s);
+				s = fma2(u2.y, d2.y, s);
+				s = fma2(u3.x, d3.x, s);
+				s = fma2(u3.y, d3.y, s);
+				c[ch] = lo2(s) + hi2(s);
+			}
 		}
 		const float S0a = lo2(S0), S0b = hi2(S0), Sxa = lo2(Sx), Sxb = hi2(Sx);
 		const float S0t = S0a + S0b, Sxt = Sxa + Sxb, Sxxt = lo2(Sxx) + hi2(Sxx);

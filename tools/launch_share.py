@@ -16,6 +16,7 @@ STAGE_OF = {
     "blend_backward_kernel": "blend_bwd", "emit_kernel": "coarse_emit", "fine_kernel": "fine_bin", "fine_scan_kernel": "fine_bin",
     "fine_plan_kernel": "fine_bin", "tile_offsets_kernel": "fine_bin", "tile_ranges_kernel": "fine_bin",
     "upsweep_kernel": "sorts", "scan_kernel": "sorts", "downsweep_kernel": "sorts",
+    "onesweep_kernel": "sorts", "radix_hist_kernel": "sorts",
 }
 
 
@@ -39,7 +40,7 @@ def main():
     for k, v in t.items():
         by_stage[STAGE_OF.get(k, k)] += v
     lines = [f"# Launch list of `python bench.py --steps 1 --warmup 3` under ncu vs the live stage times", "",
-             f"{sum(n.values())} native-kernel launches captured in steady state (`--launch-skip 1600 --launch-count 400`; file "
+             f"{sum(n.values())} native-kernel launches captured in steady state (`--launch-skip 1200 --launch-count 400`; file "
              f"`profiles/{os.path.basename(out).replace('_launch_share.md', '_launches_bench.csv')}`), "
              f"`ncu --metrics gpu__time_duration.sum --clock-control none`.  Per-launch times are cold-cache and serialised "
              "by ncu, so only the SHARE of each kernel is comparable with the CUDA-event stage times that `bench.py` "

@@ -7,7 +7,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import parity_lib as pl
 from workload import synthetic
-from bloomscene_b200.multiview import GaussianParams, view_sharded_step
+from bloomscene_b200.multiview import view_sharded_step
+from workload.params import GaussianParams
 
 dev = torch.device("cuda:0")
 api = pl.ours()
@@ -36,4 +37,32 @@ for (P, color, W, H, mu) in [(3000, "sh3", 160, 96, -3.2), (1500, "precomp", 70,
     frames = api.render_views(settings, scene.means3D, scene.opacities, scales=scene.scales, rotations=scene.rotations, **col)
     torch.cuda.synchronize()
     print("depth-grad", float(leaves["means3D"].grad.abs().sum()), "frames", float(frames[0].sum()))
+    # forward modes: optimistic with stale marks (overflow -> re-run), deferred with far too small capacities
+    _C = api._C
+    e = torch.Tensor([])
+    args = pl.forward_args(scene, cam, bg)
+    _C.reset_marks()
+    _C.rasterize_gaussians_ex(*pl.forward_args(scene, cam, bg, scale_modifier=0.3), _C.FWD_AUTO)
+    _C.rasterize_gaussians_ex(*pl.forward_args(scene, cam, bg, scale_modifier=2.5), _C.FWD_AUTO)  # overflows the marks
+    report = torch.zeros(8, dtype=torch.int32).pin_memory()
+    _C.rasterize_gaussians_ex(*args, _C.FWD_DEFERRED, 16, 8, 8, report)
+    torch.cuda.synchronize()
+    print("modes", _C.forward_stats(True), "deferred overflow word", int(report[5]))
+    _C.reset_marks()
+
+# the steps either side of the rasterizer
+from bloomscene_b200.fused import l1_ssim_loss, neural_gaussians
+g = torch.Generator().manual_seed(0)
+img = torch.rand(3, 45, 37, generator=g).to(dev).requires_grad_(True)
+l1_ssim_loss(img, torch.rand(3, 45, 37, generator=g).to(dev)).backward()
+N, K = 700, 10
+ins = [torch.randn(N, 3, generator=g), torch.rand(N, 6, generator=g), torch.randn(N, K, 3, generator=g),
+       torch.randn(N * K, 1, generator=g), torch.rand(N * K, 3, generator=g), torch.randn(N * K, 7, generator=g)]
+ins = [t.to(dev).requires_grad_(True) for t in ins]
+out = neural_gaussians(*ins)
+sum(o.sum() for o in out[:5]).backward()
+rs = synthetic.raster_settings(synthetic.orbit_camera(64, 48, 0.2).to(dev), 0, torch.zeros(3, device=dev), api.GaussianRasterizationSettings)
+sc = synthetic.make_scene(900, "band", "precomp", -3.0, seed=2).to(dev)
+print("filter", api.GaussianRasterizer(rs).visible_filter_indices(sc.means3D, sc.scales, sc.rotations)[1].numel())
+torch.cuda.synchronize()
 print("done")

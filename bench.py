@@ -46,8 +46,8 @@ N_VIEWS = 64
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch at config C, read from the
 # `ncu --set full` captures summarised under profiles/ (refreshed whenever a blend kernel changes).
 NCU_TRAFFIC = {
-    "blend_bwd": {"bytes": int((112.8 + 8.381) * 1e6), "source": "profiles/r01s7_ncu_full.md"},
-    "blend_fwd": {"bytes": int((76.46 + 23.93) * 1e6), "source": "profiles/r01s7_ncu_full.md"},
+    "blend_bwd": {"bytes": int((112.7 + 8.306) * 1e6), "source": "profiles/r02_ncu_full.md"},
+    "blend_fwd": {"bytes": int((76.57 + 23.49) * 1e6), "source": "profiles/r02_ncu_full.md"},
 }
 
 
@@ -272,9 +272,10 @@ def stage_model(P, V, R, R1, M, npix, ntile, E, C, Eb):
     R1 = (supertile, Gaussian) instances, the only thing the coarse level sorts."""
     return {
         "preprocess": ("hbm", 52 * P + (12 * M + 67) * V),
-        "depth_sort": ("hbm", (4 + 16 * 3) * P),  # one histogram read + 3 passes of 8-byte pairs (23-24 significant key bits)
-        "coarse_emit": ("hbm", 4 * P + 8 * V + 8 * R1),
-        "coarse_sort": ("hbm", (4 + 16) * R1),  # histogram read + one pass of 8-byte pairs (<= 256 supertiles)
+        # histogram reads P keys; pass 1 reads P keys, writes V pairs; pass 2 moves V pairs; pass 3 reads V pairs, writes V ids
+        "depth_sort": ("hbm", 8 * P + (8 + 16 + 12) * V),
+        "coarse_emit": ("hbm", 12 * V + 8 * R1),  # order + rect in, (supertile, id) instances out
+        "coarse_sort": ("hbm", (8 + 4) * R1),  # one pass: pairs in, ids out (digit totals come from the emission's histogram)
         "fine_bin": ("hbm", 2 * (4 + 8) * R1 + 4 * R + 16 * ntile),  # count + scatter passes read id + rect; ids written once
         "blend_fwd": ("fp32", 21 * E + 16 * C),
         "blend_bwd": ("fp32", 21 * Eb + 70 * C),

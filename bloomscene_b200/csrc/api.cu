@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -30,7 +31,7 @@ namespace brs {
 
 namespace {
 
-thread_local long long t_launches = 0;
+std::atomic<long long> g_launches{0}; // process-wide: autograd runs the backward on its own thread
 thread_local long long t_fwd_stats[4] = {0, 0, 0, 0}; // exact, optimistic, overflow re-runs, deferred
 thread_local int t_last_cuda_error = 0;
 
@@ -295,7 +296,7 @@ int validate_gaussians(const brs_view* v, const brs_gaussians* g)
 
 } // namespace
 
-void count_launch() { t_launches++; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 } // namespace brs
 
@@ -307,9 +308,7 @@ int brs_version(void) { return BRS_VERSION; }
 
 long long brs_launch_count(int reset)
 {
-	long long v = t_launches;
-	if (reset)
-		t_launches = 0;
+	const long long v = reset ? g_launches.exchange(0) : g_launches.load();
 	return v;
 }
 

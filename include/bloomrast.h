@@ -255,7 +255,7 @@ const char* brs_error_string(int status);
 int brs_last_cuda_error(void);
 const char* brs_last_cuda_error_string(void);
 int brs_version(void);
-/* Number of kernels this library launched on the calling thread since the last reset. */
+/* Number of kernels this library launched (process-wide, all threads) since the last reset. */
 long long brs_launch_count(int reset);
 
 /* --- the steps either side of the rasterizer (extensions; opt-in) ------------------- */

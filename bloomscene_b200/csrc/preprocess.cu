@@ -185,9 +185,9 @@ __device__ __forceinline__ void stage_camera(float* s_cam, const float* view, co
 }
 
 // VEC: rows are 16 coefficient triples (48 floats = 12 float4 = 192 bytes) and `shs` is 16-byte aligned.  Every
-//   lane then fetches ITS row with one bulk asynchronous copy (cp.async.bulk -> SASS UBLKCP) into a pitch-13
-//   float4 shared-memory tile (lane-consecutive LDS.128 rows are conflict-free); the bytes are collected by one
-//   mbarrier per warp, so there is no block barrier between the geometry, load and evaluation phases and no
+//   pair of rows is fetched with one bulk asynchronous copy (cp.async.bulk -> SASS UBLKCP, 384 bytes) into a
+//   shared-memory tile whose pair pitch makes the lanes' LDS.128 reads conflict-free (sh_row_slot, common.cuh);
+//   the bytes are collected by one mbarrier per warp, so there is no block barrier between the geometry, load and evaluation phases and no
 //   SH data passes through registers on its way in.
 // EAGER: the rows of ALL 32 Gaussians of the warp are requested at the very start, together with the
 //   geometry inputs, so that a thread exposes one DRAM round trip instead of two; otherwise only the rows of
@@ -212,9 +212,10 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 			mbar_init(&s_bar[warp], 1);
 		__syncwarp();
 		if (EAGER) {
+			// even lanes fetch their own row and their neighbour's (one 384-byte copy; 192 at the end of the array)
 			const uint32_t rows = (uint32_t)max(0, min(32, a.P - (block_first + 32 * warp)));
-			if (in_range)
-				bulk_copy_g2s(s_dyn + threadIdx.x * 13, a.shs + (size_t)idx * 48, 192u, &s_bar[warp]);
+			if (in_range && !(lane & 1))
+				bulk_copy_g2s(s_dyn + sh_row_slot(threadIdx.x), a.shs + (size_t)idx * 48, idx + 1 < a.P ? 384u : 192u, &s_bar[warp]);
 			if (lane == 0)
 				mbar_arrive_expect_tx(&s_bar[warp], 192u * rows);
 		}
@@ -257,10 +258,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 		const int warp_first = block_first + 32 * warp;
 		if (VEC) {
 			if (!EAGER) {
-				if (visible)
-					bulk_copy_g2s(s_dyn + threadIdx.x * 13, a.shs + (size_t)idx * 48, 192u, &s_bar[warp]);
+				// a pair of rows is fetched (by its even lane) when either of its Gaussians is visible
+				const uint32_t pair_mask = (vis_mask | (vis_mask >> 1)) & 0x55555555u;
+				const uint32_t short_pair = (in_range && !(lane & 1) && idx + 1 >= a.P && ((pair_mask >> lane) & 1u)) ? 1u : 0u;
+				if (in_range && ((pair_mask >> lane) & 1u))
+					bulk_copy_g2s(s_dyn + sh_row_slot(threadIdx.x), a.shs + (size_t)idx * 48, short_pair ? 192u : 384u, &s_bar[warp]);
+				const uint32_t shorts = __popc(__ballot_sync(0xffffffffu, short_pair != 0u));
 				if (lane == 0)
-					mbar_arrive_expect_tx(&s_bar[warp], 192u * (uint32_t)__popc(vis_mask));
+					mbar_arrive_expect_tx(&s_bar[warp], 384u * (uint32_t)__popc(pair_mask) - 192u * shorts);
 			}
 			if (vis_mask != 0u || EAGER)
 				mbar_wait(&s_bar[warp], 0u);
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 			v3 res;
 			if (VEC) {
 				// coefficients are read from the staged row where they are used (conflict-free LDS.128)
-				res = eval_sh(a.D, pos, cam, ShRowView{s_dyn + threadIdx.x * 13});
+				res = eval_sh(a.D, pos, cam, ShRowView{s_dyn + sh_row_slot(threadIdx.x)});
 			} else {
 				res = eval_sh(a.D, pos, cam, reinterpret_cast<const float*>(s_dyn) + threadIdx.x * (row_f | 1));
 			}
@@ -474,7 +479,7 @@ cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream)
 	bool vec = false;
 	if (a.shs != nullptr) {
 		vec = (a.M == 16) && ((reinterpret_cast<uintptr_t>(a.shs) & 15u) == 0);
-		smem = vec ? (size_t)PRE_THREADS * 13 * sizeof(float4) : (size_t)PRE_THREADS * ((3 * a.M) | 1) * sizeof(float);
+		smem = vec ? (size_t)(PRE_THREADS / 2) * SH_PAIR_PITCH * sizeof(float4) : (size_t)PRE_THREADS * ((3 * a.M) | 1) * sizeof(float);
 	}
 	if (vec && a.eager_sh)
 		preprocess_kernel<true, true><<<blocks, PRE_THREADS, smem, stream>>>(a);

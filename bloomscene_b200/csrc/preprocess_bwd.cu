@@ -63,9 +63,10 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 			mbar_init(&s_bar[warp], 1);
 		__syncwarp();
 		if (EAGER) {
+			// even lanes fetch their own row and their neighbour's (one 384-byte copy; 192 at the end of the array)
 			const uint32_t rows = (uint32_t)max(0, min(32, a.P - (block_first + 32 * warp)));
-			if (in_range)
-				bulk_copy_g2s(s_dyn + threadIdx.x * 13, a.shs + (size_t)idx * 48, 192u, &s_bar[warp]);
+			if (in_range && !(lane & 1))
+				bulk_copy_g2s(s_dyn + sh_row_slot(threadIdx.x), a.shs + (size_t)idx * 48, idx + 1 < a.P ? 384u : 192u, &s_bar[warp]);
 			if (lane == 0)
 				mbar_arrive_expect_tx(&s_bar[warp], 192u * rows);
 		}
@@ -115,10 +116,14 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 	if (a.shs != nullptr) {
 		if (VEC) {
 			if (!EAGER) {
-				if (visible)
-					bulk_copy_g2s(s_dyn + threadIdx.x * 13, a.shs + (size_t)idx * 48, 192u, &s_bar[warp]);
+				// a pair of rows is fetched (by its even lane) when either of its Gaussians was rendered
+				const uint32_t pair_mask = (vis_mask | (vis_mask >> 1)) & 0x55555555u;
+				const uint32_t short_pair = (in_range && !(lane & 1) && idx + 1 >= a.P && ((pair_mask >> lane) & 1u)) ? 1u : 0u;
+				if (in_range && ((pair_mask >> lane) & 1u))
+					bulk_copy_g2s(s_dyn + sh_row_slot(threadIdx.x), a.shs + (size_t)idx * 48, short_pair ? 192u : 384u, &s_bar[warp]);
+				const uint32_t shorts = __popc(__ballot_sync(0xffffffffu, short_pair != 0u));
 				if (lane == 0)
-					mbar_arrive_expect_tx(&s_bar[warp], 192u * (uint32_t)__popc(vis_mask));
+					mbar_arrive_expect_tx(&s_bar[warp], 384u * (uint32_t)__popc(pair_mask) - 192u * shorts);
 			}
 		} else {
 			const int pitch = row_f | 1;
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(PB_THREADS, 6) preprocess_backward_kernel(Prep
 			V3 g_rgb;
 			float q[16];
 			if (VEC) {
-				const ShRowView c{s_dyn + threadIdx.x * 13};
+				const ShRowView c{s_dyn + sh_row_slot(threadIdx.x)};
 				const v3 rgb = eval_sh(a.D, pos, cam, c);
 				g_rgb = vec3(rgb.x < 0 ? 0.f : o_color.x, rgb.y < 0 ? 0.f : o_color.y, rgb.z < 0 ? 0.f : o_color.z);
 #pragma unroll
@@ -356,7 +361,7 @@ cudaError_t launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t 
 	if (a.shs != nullptr) {
 		vec = (a.M == 16) && ((reinterpret_cast<uintptr_t>(a.shs) & 15u) == 0) &&
 		      ((reinterpret_cast<uintptr_t>(a.dL_dsh) & 15u) == 0);
-		in = vec ? (size_t)PB_THREADS * 13 * sizeof(float4) : align_up((size_t)PB_THREADS * ((3 * a.M) | 1) * sizeof(float), 16);
+		in = vec ? align_up((size_t)(PB_THREADS / 2) * SH_PAIR_PITCH * sizeof(float4), 16) : align_up((size_t)PB_THREADS * ((3 * a.M) | 1) * sizeof(float), 16);
 	}
 	PreprocessBwdArgs args = a;
 	args.fact_offset = (int)(in / sizeof(float));

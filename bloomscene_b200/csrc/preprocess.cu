@@ -129,6 +129,12 @@ __device__ __forceinline__ bool compute_geometry(const GeomInputs& in, const flo
 	get_rect(point_image, my_radius, rect_min, rect_max, grid_x, grid_y);
 	if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0)
 		return false;
+	// A finite covariance always gives my_radius >= 1 (lambda1 >= mid + sqrt(0.1)).  A NaN covariance gives
+	// (int)NaN = 0 with a one-tile rect: the reference then counts an instance in tiles_touched that
+	// duplicateWithKeys never writes (`if (radii[idx] > 0)`, rasterizer_impl.cu:89) and sorts an uninitialised
+	// key slot.  Treat it as culled, which is what `radii == 0` tells every caller anyway.
+	if ((int)my_radius <= 0)
+		return false;
 
 	g.depth = p_view.z;
 	g.xy = point_image;

@@ -191,6 +191,72 @@ def test_edge_cases_vs_reference_cuda():
     _assert_stage_parity(pl.compare_stages(s, synthetic.orbit_camera(320, 200, 0.9).to(DEV), bg))
 
 
+def test_non_finite_inputs_vs_reference_cuda():
+    """Non-finite parameters (a diverged optimisation).  Geometry, keys and lists stay bit-identical; a non-finite
+    OPACITY or CONIC behaves as in the reference (fminf(0.99, NaN) = 0.99 on both sides, the culling test lets NaNs
+    pass).  A non-finite COLOUR is the one documented difference: the reference poisons the pixels
+    the Gaussian contributes to, the branch-free blend poisons the 8x8 pixel blocks it contributes to — a superset,
+    and everything outside it is unchanged."""
+    ref = _ref_or_skip()
+    mine = pl.ours()
+    cam = synthetic.orbit_camera(96, 64, 0.2).to(DEV)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+
+    def render(api, s):
+        R, color, depth, radii, *_ = api._C.rasterize_gaussians(*pl.forward_args(s, cam, bg))
+        torch.cuda.synchronize()
+        return R, color, depth, radii
+
+    # opacity / position NaN: identical behaviour
+    s = synthetic.make_scene(600, "object", "precomp", -3.2, seed=12)
+    s.opacities[20] = float("nan")
+    s.opacities[21] = float("inf")
+    s.means3D[40, 0] = float("nan")
+    s = s.to(DEV)
+    rep = pl.compare_stages(s, cam, bg)
+    assert rep["point_list_mismatch"] == 0 and rep["ranges_mismatch"] == 0 and rep["n_contrib_mismatch"] == 0, rep
+    Ro, co, do, ro = render(mine, s)
+    Rr, cr, dr, rr = render(ref, s)
+    assert Ro == Rr and torch.equal(ro, rr)
+    assert torch.equal(torch.isfinite(co), torch.isfinite(cr))
+    ok = torch.isfinite(cr)
+    assert (co[ok] - cr[ok]).abs().max().item() <= pl.COLOR_TOL
+    okd = torch.isfinite(dr)
+    assert torch.equal(torch.isfinite(do), okd) and (do[okd] - dr[okd]).abs().max().item() <= pl.COLOR_TOL
+
+    # NaN scale -> NaN covariance -> radius (int)NaN = 0 with a one-tile rect.  The reference counts that instance but
+    # never writes its key (`if (radii[idx] > 0)`, rasterizer_impl.cu:85) and sorts an uninitialised slot; here the
+    # Gaussian is culled: same image as with the Gaussian behind the camera.
+    s = synthetic.make_scene(600, "object", "precomp", -3.2, seed=12)
+    t = synthetic.make_scene(600, "object", "precomp", -3.2, seed=12)
+    s.scales[30, 1] = float("nan")
+    t.means3D[30, 2] -= 100.0
+    Rs, cs, ds, rs = render(mine, s.to(DEV))
+    Rt, ct, dt, rt = render(mine, t.to(DEV))
+    assert Rs == Rt and torch.equal(rs, rt) and rs[30] == 0 and torch.equal(cs, ct) and torch.equal(ds, dt)
+
+    # colour NaN / inf: superset within 8x8 blocks
+    s = synthetic.make_scene(600, "object", "precomp", -3.2, seed=13)
+    s.scales[:] *= 0.5
+    s.colors_precomp[5, 1] = float("nan")
+    s.colors_precomp[9, 0] = float("inf")
+    s = s.to(DEV)
+    Ro, co, do, ro = render(mine, s)
+    Rr, cr, dr, rr = render(ref, s)
+    assert Ro == Rr and torch.equal(ro, rr)
+    bad_ref = ~torch.isfinite(cr).all(0)
+    bad_ours = ~torch.isfinite(co).all(0)
+    assert bad_ref.any() and not bad_ref.all()
+    assert not (bad_ref & ~bad_ours).any()                       # superset
+    H, W = bad_ref.shape
+    blocks = torch.nn.functional.max_pool2d(bad_ref[None, None].float(), 8, 8, ceil_mode=True)
+    dil = torch.nn.functional.interpolate(blocks, scale_factor=8, mode="nearest")[0, 0, :H, :W] > 0
+    assert not (bad_ours & ~dil).any()                           # ... confined to the touched 8x8 blocks
+    good = ~bad_ours
+    assert (co[:, good] - cr[:, good]).abs().max().item() <= pl.COLOR_TOL
+    assert (do - dr).abs().max().item() <= pl.COLOR_TOL          # depth does not see colours
+
+
 def test_debug_flag_and_python_api_shapes():
     mine = pl.ours()
     scene = synthetic.make_scene(2000, "object", "sh3", -3.5, seed=2).to(DEV)

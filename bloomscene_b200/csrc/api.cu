@@ -236,7 +236,7 @@ GeomLayout geom_layout(size_t P)
 struct ImageLayout {
 	size_t ranges, final_T, n_contrib, total;
 };
-ImageLayout image_layout(int W, int H)
+ImageLayout image_layout(int W, int H, bool pixel_state = true)
 {
 	ImageLayout l{};
 	const size_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
@@ -245,9 +245,9 @@ ImageLayout image_layout(int W, int H)
 	l.ranges = off;
 	off += align_up(sizeof(uint2) * gx * gy, 256);
 	l.final_T = off;
-	off += align_up(sizeof(float) * npix, 256);
+	off += pixel_state ? align_up(sizeof(float) * npix, 256) : 0;
 	l.n_contrib = off;
-	off += align_up(sizeof(uint32_t) * npix, 256);
+	off += pixel_state ? align_up(sizeof(uint32_t) * npix, 256) : 0;
 	l.total = off < 256 ? 256 : off;
 	return l;
 }
@@ -502,9 +502,10 @@ Caps caps_from_marks(const Marks& m)
 }
 
 struct ForwardCtx {
-	const brs_view* view;
-	int P, W, H;
-	uint32_t grid_x, grid_y;
+	const brs_view* view; // n_views of them
+	int n_views;          // > 1: a stack of views rendered as one pipeline (brs_forward_views)
+	int P, W, H;          // P: Gaussians per view; the pipeline works on n_views * P instances
+	uint32_t grid_x, grid_y; // tiles of ONE view; the stack has n_views * grid_y tile rows
 	bool debug;
 	brs_alloc_fn alloc;
 	void* alloc_ctx;
@@ -533,14 +534,16 @@ int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* r
 	c.state->binning = binning;
 	c.state->binning_bytes = binning_bytes(caps.R_cap);
 
+	const size_t P_inst = (size_t)c.P * c.n_views;          // instances: (view, Gaussian)
+	const uint32_t rows = c.grid_y * (uint32_t)c.n_views;   // tile rows of the stack of views
 	BinPlan pl{};
-	pl.P = (uint32_t)c.P;
+	pl.P = (uint32_t)P_inst;
 	pl.R1_cap = caps.R1_cap;
 	pl.R_cap = caps.R_cap;
 	pl.grid_x = c.grid_x;
-	pl.grid_y = c.grid_y;
+	pl.grid_y = rows;
 	pl.ns_x = supertiles(c.grid_x);
-	pl.ns = pl.ns_x * supertiles(c.grid_y);
+	pl.ns = pl.ns_x * supertiles(rows);
 	pl.depth_passes = caps.depth_passes;
 	pl.hdr = hdr;
 	pl.depth_key = reinterpret_cast<const uint32_t*>(c.geom + c.gl.depth_key);
@@ -550,17 +553,17 @@ int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* r
 	pl.ranges = reinterpret_cast<uint2*>(c.image + c.il.ranges);
 	pl.overflow_accum = overflow_accum;
 
-	const bool have_grid = c.grid_x * c.grid_y > 0;
+	const bool have_grid = c.grid_x * rows > 0;
 	if (have_grid) {
-		const size_t dz = depth_zero_bytes(c.P, caps.depth_passes), iz = inst_zero_bytes(c.P, caps.R1_cap, c.grid_x, c.grid_y);
-		const size_t dp = depth_plain_bytes(c.P);
+		const size_t dz = depth_zero_bytes(P_inst, caps.depth_passes), iz = inst_zero_bytes(P_inst, caps.R1_cap, c.grid_x, rows);
+		const size_t dp = depth_plain_bytes(P_inst);
 		char* scratch = static_cast<char*>(
-		    c.alloc(c.alloc_ctx, BRS_BUF_SCRATCH, forward_scratch_bytes(c.P, caps.R1_cap, c.grid_x, c.grid_y, caps.depth_passes)));
+		    c.alloc(c.alloc_ctx, BRS_BUF_SCRATCH, forward_scratch_bytes(P_inst, caps.R1_cap, c.grid_x, rows, caps.depth_passes)));
 		if (scratch == nullptr)
 			return BRS_ERR_ALLOC;
 		BRS_CUDA(cudaMemsetAsync(scratch, 0, dz + iz, stream)); // tickets, histograms, look-back status words
-		pl.d = carve_depth_scratch(scratch, scratch + dz + iz, c.P, caps.depth_passes);
-		pl.i = carve_inst_scratch(scratch + dz, scratch + dz + iz + dp, c.P, caps.R1_cap, c.grid_x, c.grid_y);
+		pl.d = carve_depth_scratch(scratch, scratch + dz + iz, P_inst, caps.depth_passes);
+		pl.i = carve_inst_scratch(scratch + dz, scratch + dz + iz + dp, P_inst, caps.R1_cap, c.grid_x, rows);
 
 		BRS_STAGE(BRS_STAGE_DEPTH_SORT, launch_depth_sort_begin(pl, caps.depth_passes, stream), debug, stream);
 		if (report != nullptr) {
@@ -588,8 +591,10 @@ int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* r
 	ba.H = c.H;
 	ba.grid_x = c.grid_x;
 	ba.grid_y = c.grid_y;
-	ba.final_T = reinterpret_cast<float*>(c.image + c.il.final_T);
-	ba.n_contrib = reinterpret_cast<uint32_t*>(c.image + c.il.n_contrib);
+	ba.views = c.n_views;
+	// a stack of views is forward-only: the per-pixel state the backward needs is not kept
+	ba.final_T = c.n_views > 1 ? nullptr : reinterpret_cast<float*>(c.image + c.il.final_T);
+	ba.n_contrib = c.n_views > 1 ? nullptr : reinterpret_cast<uint32_t*>(c.image + c.il.n_contrib);
 	ba.out_color = c.out_color;
 	ba.out_depth = c.out_depth;
 	Companion comp;
@@ -605,23 +610,27 @@ int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* r
 	return BRS_OK;
 }
 
-} // namespace
-
-extern "C" {
-
-int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, float* out_depth, int* radii,
-                brs_alloc_fn alloc, void* alloc_ctx, brs_fwd_state* state, brs_stream stream)
+// One forward over a stack of n_views views of the same Gaussians (n_views == 1: brs_forward_ex).  The views'
+// preprocess launches write into ONE instance space — instance v * P + i is Gaussian i seen from view v, its
+// tile rectangle shifted down by v * grid_y rows — so that everything behind it (depth sort, emission, coarse
+// sort, fine binning, blend) runs once over all views.
+int forward_impl(const brs_view* views, int n_views, const brs_gaussians* g, float* out_color, float* out_depth, int* radii,
+                 brs_alloc_fn alloc, void* alloc_ctx, brs_fwd_state* state, const brs_fwd_options* opt, cudaStream_t stream)
 {
-	return brs_forward_ex(view, g, out_color, out_depth, radii, alloc, alloc_ctx, state, nullptr, stream);
-}
-
-int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_color, float* out_depth, int* radii,
-                   brs_alloc_fn alloc, void* alloc_ctx, brs_fwd_state* state, const brs_fwd_options* opt, brs_stream stream)
-{
-	int st = validate_view(view, true);
-	if (st != BRS_OK)
-		return st;
-	st = validate_gaussians(view, g);
+	const brs_view* view = views;
+	if (views == nullptr || n_views < 1 || n_views > 65535)
+		return BRS_ERR_INVALID_ARG;
+	int st = BRS_OK;
+	for (int v = 0; v < n_views && st == BRS_OK; v++) {
+		st = validate_view(views + v, true);
+		if (st == BRS_OK)
+			st = validate_gaussians(views + v, g);
+		// one image size, one SH layout and one debug flag for the whole stack; the background of views[0] is used
+		if (st == BRS_OK && (views[v].image_width != view->image_width || views[v].image_height != view->image_height ||
+		                     views[v].sh_degree != view->sh_degree || views[v].sh_coeffs != view->sh_coeffs ||
+		                     views[v].debug != view->debug))
+			st = BRS_ERR_INVALID_ARG;
+	}
 	if (st != BRS_OK)
 		return st;
 	if (alloc == nullptr || state == nullptr)
@@ -639,7 +648,10 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 	if (mode == BRS_FWD_DEFERRED && opt->report == nullptr && opt->overflow_accum == nullptr)
 		return BRS_ERR_INVALID_ARG;
 	const int W = view->image_width, H = view->image_height, P = g->P;
-	const size_t npix = (size_t)W * H;
+	const size_t npix = (size_t)W * H * n_views;
+	const size_t P_inst = (size_t)P * n_views;
+	if (P_inst > (1ull << 31) - 1 || (size_t)((H + TILE_Y - 1) / TILE_Y) * n_views >= 65536)
+		return BRS_ERR_UNSUPPORTED; // instance ids are 32-bit, tile rows of the stack are packed into 16 bits
 	if ((npix > 0 && (out_color == nullptr || out_depth == nullptr)) || (P > 0 && radii == nullptr))
 		return BRS_ERR_INVALID_ARG;
 	const bool debug = view->debug != 0;
@@ -660,6 +672,7 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 
 	ForwardCtx c{};
 	c.view = view;
+	c.n_views = n_views;
 	c.P = P;
 	c.W = W;
 	c.H = H;
@@ -670,8 +683,8 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 	c.alloc_ctx = alloc_ctx;
 	c.state = state;
 	c.stream = stream;
-	c.gl = geom_layout(P);
-	c.il = image_layout(W, H);
+	c.gl = geom_layout(P_inst);
+	c.il = n_views > 1 ? image_layout(W, (int)(c.grid_y * n_views * TILE_Y), false) : image_layout(W, H);
 	c.out_color = out_color;
 	c.out_depth = out_depth;
 
@@ -699,31 +712,36 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 	pa.shs = g->shs;
 	pa.cov3D_precomp = g->cov3D_precomp;
 	pa.colors_precomp = g->colors_precomp;
-	pa.viewmatrix = view->viewmatrix;
-	pa.projmatrix = view->projmatrix;
-	pa.campos = view->campos;
 	pa.W = W;
 	pa.H = H;
-	pa.tan_fovx = view->tanfovx;
-	pa.tan_fovy = view->tanfovy;
-	pa.focal_y = H / (2.0f * view->tanfovy); // rasterizer_impl.cu:223-224
-	pa.focal_x = W / (2.0f * view->tanfovx);
 	pa.grid_x = c.grid_x;
 	pa.grid_y = c.grid_y;
-	pa.prefiltered = view->prefiltered;
-	pa.radii = radii;
-	pa.records = reinterpret_cast<float4*>(c.geom + c.gl.records);
-	pa.depth_key = reinterpret_cast<uint32_t*>(c.geom + c.gl.depth_key);
-	pa.rect = reinterpret_cast<uint2*>(c.geom + c.gl.rect);
 	pa.total_tiles = hdr;
 	int dev = 0;
 	BRS_CUDA(cudaGetDevice(&dev));
-	const MarksKey key{dev, P, W, H};
+	const MarksKey key{dev, (int)P_inst, W, H * n_views};
 	Marks marks;
 	const bool have_marks = lookup_marks(key, marks);
 	// SH rows: requested for all Gaussians up front when most of them were visible in the last views of this shape
-	pa.eager_sh = (have_marks && 2ull * marks.V > (unsigned long long)P) ? 1 : 0;
-	BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
+	pa.eager_sh = (have_marks && 2ull * marks.V > (unsigned long long)P_inst) ? 1 : 0;
+	for (int v = 0; v < n_views; v++) {
+		const brs_view* vw = views + v;
+		pa.scale_modifier = vw->scale_modifier;
+		pa.viewmatrix = vw->viewmatrix;
+		pa.projmatrix = vw->projmatrix;
+		pa.campos = vw->campos;
+		pa.tan_fovx = vw->tanfovx;
+		pa.tan_fovy = vw->tanfovy;
+		pa.focal_y = H / (2.0f * vw->tanfovy); // rasterizer_impl.cu:223-224
+		pa.focal_x = W / (2.0f * vw->tanfovx);
+		pa.prefiltered = vw->prefiltered;
+		pa.row_offset = (uint32_t)v * c.grid_y;
+		pa.radii = radii + (size_t)v * P;
+		pa.records = reinterpret_cast<float4*>(c.geom + c.gl.records) + 3 * (size_t)v * P;
+		pa.depth_key = reinterpret_cast<uint32_t*>(c.geom + c.gl.depth_key) + (size_t)v * P;
+		pa.rect = reinterpret_cast<uint2*>(c.geom + c.gl.rect) + (size_t)v * P;
+		BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
+	}
 
 	// ---- deferred: the caller's capacities (or the high-water marks), no host wait at all ----
 	if (mode == BRS_FWD_DEFERRED) {
@@ -788,6 +806,33 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_colo
 	state->num_rendered = (int)R;
 	raise_marks(key, R, R1, key_bits, V);
 	return enqueue_binning_and_blend(c, caps, nullptr, nullptr);
+}
+
+} // namespace
+
+extern "C" {
+
+int brs_forward(const brs_view* view, const brs_gaussians* g, float* out_color, float* out_depth, int* radii,
+                brs_alloc_fn alloc, void* alloc_ctx, brs_fwd_state* state, brs_stream stream)
+{
+	return brs_forward_ex(view, g, out_color, out_depth, radii, alloc, alloc_ctx, state, nullptr, stream);
+}
+
+int brs_forward_ex(const brs_view* view, const brs_gaussians* g, float* out_color, float* out_depth, int* radii,
+                   brs_alloc_fn alloc, void* alloc_ctx, brs_fwd_state* state, const brs_fwd_options* opt, brs_stream stream)
+{
+	return forward_impl(view, 1, g, out_color, out_depth, radii, alloc, alloc_ctx, state, opt, stream);
+}
+
+int brs_forward_views(const brs_view* views, int n_views, const brs_gaussians* g, float* out_color, float* out_depth,
+                      int* radii, brs_alloc_fn alloc, void* alloc_ctx, long long* num_rendered, const brs_fwd_options* opt,
+                      brs_stream stream)
+{
+	brs_fwd_state st{};
+	const int rc = forward_impl(views, n_views, g, out_color, out_depth, radii, alloc, alloc_ctx, &st, opt, stream);
+	if (num_rendered != nullptr)
+		*num_rendered = st.num_rendered;
+	return rc;
 }
 
 void brs_forward_stats(long long* out, int reset)

@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 	const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 7);
 
 	const ExpConsts ek = {a.exp_c_scale, a.exp_c_252};
-	const uint2 range = __ldg(a.ranges + tile_y * a.grid_x + tile_x);
+	const uint32_t view = blockIdx.z; // a stack of views: tile rows [view * grid_y, (view + 1) * grid_y) of `ranges`
+	const uint2 range = __ldg(a.ranges + (view * a.grid_y + tile_y) * a.grid_x + tile_x);
 	const int n = (int)(range.y - range.x);
 	const uint32_t* list = a.point_list + range.x;
 
@@ -156,23 +157,29 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 
 	const size_t plane = (size_t)a.W * a.H;
 	const float bg0 = __ldg(a.bg + 0), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
+	float* out_color = a.out_color + view * (NUM_CHANNELS * plane);
+	const size_t pix_base = view * plane;
 	if (inside0) {
 		const uint32_t pix_id = (uint32_t)a.W * py0 + px;
-		a.final_T[pix_id] = T.lo;
-		a.n_contrib[pix_id] = last0;
-		a.out_color[pix_id] = __fmaf_rn(bg0, T.lo, C0.lo);
-		a.out_color[plane + pix_id] = __fmaf_rn(bg1, T.lo, C1.lo);
-		a.out_color[2 * plane + pix_id] = __fmaf_rn(bg2, T.lo, C2.lo);
-		a.out_depth[pix_id] = (acc.lo > 0.5f) ? __fdiv_rn(D.lo, acc.lo) : 0.0f;
+		if (a.final_T != nullptr) {
+			a.final_T[pix_base + pix_id] = T.lo;
+			a.n_contrib[pix_base + pix_id] = last0;
+		}
+		out_color[pix_id] = __fmaf_rn(bg0, T.lo, C0.lo);
+		out_color[plane + pix_id] = __fmaf_rn(bg1, T.lo, C1.lo);
+		out_color[2 * plane + pix_id] = __fmaf_rn(bg2, T.lo, C2.lo);
+		a.out_depth[pix_base + pix_id] = (acc.lo > 0.5f) ? __fdiv_rn(D.lo, acc.lo) : 0.0f;
 	}
 	if (inside1) {
 		const uint32_t pix_id = (uint32_t)a.W * py1 + px;
-		a.final_T[pix_id] = T.hi;
-		a.n_contrib[pix_id] = last1;
-		a.out_color[pix_id] = __fmaf_rn(bg0, T.hi, C0.hi);
-		a.out_color[plane + pix_id] = __fmaf_rn(bg1, T.hi, C1.hi);
-		a.out_color[2 * plane + pix_id] = __fmaf_rn(bg2, T.hi, C2.hi);
-		a.out_depth[pix_id] = (acc.hi > 0.5f) ? __fdiv_rn(D.hi, acc.hi) : 0.0f;
+		if (a.final_T != nullptr) {
+			a.final_T[pix_base + pix_id] = T.hi;
+			a.n_contrib[pix_base + pix_id] = last1;
+		}
+		out_color[pix_id] = __fmaf_rn(bg0, T.hi, C0.hi);
+		out_color[plane + pix_id] = __fmaf_rn(bg1, T.hi, C1.hi);
+		out_color[2 * plane + pix_id] = __fmaf_rn(bg2, T.hi, C2.hi);
+		a.out_depth[pix_base + pix_id] = (acc.hi > 0.5f) ? __fdiv_rn(D.hi, acc.hi) : 0.0f;
 	}
 }
 
@@ -186,7 +193,7 @@ cudaError_t launch_blend_forward(const BlendFwdArgs& args, cudaStream_t stream)
 	a.exp_c_252 = ek.c_252;
 	if (a.W <= 0 || a.H <= 0)
 		return cudaSuccess;
-	dim3 grid(a.grid_x, a.grid_y, 1);
+	dim3 grid(a.grid_x, a.grid_y, a.views > 1 ? a.views : 1);
 	blend_forward_kernel<<<grid, BLEND_THREADS, 0, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();

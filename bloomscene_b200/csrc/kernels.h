@@ -27,6 +27,7 @@ struct PreprocessArgs {
 	uint32_t grid_x, grid_y;
 	int prefiltered;
 	int eager_sh;         // request every Gaussian's SH row up front (most are visible) instead of the visible ones' later
+	uint32_t row_offset;  // tile rows added to the rectangle: this view's place in a stack of views (brs_forward_views), else 0
 	// outputs
 	int* radii;
 	float4* records;      // [3P]
@@ -153,8 +154,9 @@ struct BlendFwdArgs {
 	const float* bg;
 	int W, H;
 	uint32_t grid_x, grid_y;
-	float* final_T;
-	uint32_t* n_contrib;
+	int views;     // > 1: `ranges` holds views * grid_y tile rows (a stack of views, brs_forward_views); outputs are [views][...]
+	float* final_T;      // nullptr: not kept (forward-only)
+	uint32_t* n_contrib; // nullptr: not kept
 	float* out_color;
 	float* out_depth;
 };

@@ -250,6 +250,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
 	uint32_t tiles = 0u, cells = 0u; // tile / supertile instances of this Gaussian
 	if (visible) {
+		g.rect_min.y += a.row_offset; // the view's place in a stack of views (0 for a single view)
+		g.rect_max.y += a.row_offset;
 		tiles = (g.rect_max.y - g.rect_min.y) * (g.rect_max.x - g.rect_min.x);
 		cells = ((((g.rect_max.x - 1) >> ST_SHIFT) + 1) - (g.rect_min.x >> ST_SHIFT)) *
 		        ((((g.rect_max.y - 1) >> ST_SHIFT) + 1) - (g.rect_min.y >> ST_SHIFT));

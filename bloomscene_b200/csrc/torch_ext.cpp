@@ -181,6 +181,82 @@ ForwardTuple RasterizeGaussiansCUDA(const torch::Tensor& background, const torch
 	                                prefiltered, debug, BRS_FWD_AUTO, 0, 0, 0, c10::nullopt, c10::nullopt);
 }
 
+// Extension (brs_forward_views): n views of the same Gaussians as ONE pipeline, forward only.
+// viewmatrices / projmatrices [n,4,4], camposes [n,3], tan_fovx / tan_fovy one value per view (or one for all).
+// Returns (instances of all views, color [n,3,H,W], depth [n,1,H,W], radii [n,P]).
+std::tuple<int64_t, torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansViewsCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                            const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                            const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrices,
+                            const torch::Tensor& projmatrices, const std::vector<double>& tan_fovx,
+                            const std::vector<double>& tan_fovy, const int image_height, const int image_width,
+                            const torch::Tensor& sh, const int degree, const torch::Tensor& camposes, const bool prefiltered,
+                            const bool debug, const int mode)
+{
+	TORCH_CHECK(means3D.ndimension() == 2 && means3D.size(1) == 3, "means3D must have dimensions (num_points, 3)");
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
+	TORCH_CHECK(viewmatrices.ndimension() == 3 && viewmatrices.size(1) == 4 && viewmatrices.size(2) == 4,
+	            "viewmatrices must have dimensions (views, 4, 4)");
+	const int n = (int)viewmatrices.size(0);
+	TORCH_CHECK(n >= 1, "at least one view");
+	TORCH_CHECK(projmatrices.sizes() == viewmatrices.sizes(), "projmatrices must have dimensions (views, 4, 4)");
+	TORCH_CHECK((tan_fovx.size() == 1 || (int)tan_fovx.size() == n) && (tan_fovy.size() == 1 || (int)tan_fovy.size() == n),
+	            "tan_fovx / tan_fovy: one value, or one per view");
+	c10::cuda::CUDAGuard guard(means3D.device());
+
+	const int P = means3D.size(0), H = image_height, W = image_width;
+	auto float_opts = means3D.options().dtype(torch::kFloat32);
+	torch::Tensor out_color = torch::empty({n, 3, H, W}, float_opts);
+	torch::Tensor out_depth = torch::empty({n, 1, H, W}, float_opts);
+	torch::Tensor radii = torch::empty({n, P}, means3D.options().dtype(torch::kInt32));
+
+	AllocCtx ctx;
+	ctx.byte_opts = torch::TensorOptions(torch::kByte).device(means3D.device());
+
+	torch::Tensor k[11];
+	const float* bg = req_ptr(background, k[0], "bg");
+	const float* vm = req_ptr(viewmatrices, k[1], "viewmatrices");
+	const float* pm = req_ptr(projmatrices, k[2], "projmatrices");
+	const float* cp = opt_ptr(camposes, k[3], "camposes");
+	TORCH_CHECK(cp == nullptr || (camposes.numel() == 3 * (int64_t)n), "camposes must have dimensions (views, 3)");
+
+	brs_gaussians g{};
+	g.P = P;
+	g.means3D = req_ptr(means3D, k[4], "means3D");
+	g.opacities = P ? req_ptr(opacity, k[5], "opacities") : nullptr;
+	g.shs = opt_ptr(sh, k[6], "shs");
+	g.colors_precomp = opt_ptr(colors, k[7], "colors_precomp");
+	g.scales = opt_ptr(scales, k[8], "scales");
+	g.rotations = opt_ptr(rotations, k[9], "rotations");
+	g.cov3D_precomp = opt_ptr(cov3D_precomp, k[10], "cov3D_precomp");
+
+	std::vector<brs_view> views((size_t)n);
+	for (int v = 0; v < n; v++) {
+		brs_view& view = views[(size_t)v];
+		view = brs_view{};
+		view.image_width = W;
+		view.image_height = H;
+		view.tanfovx = (float)tan_fovx[tan_fovx.size() == 1 ? 0 : (size_t)v];
+		view.tanfovy = (float)tan_fovy[tan_fovy.size() == 1 ? 0 : (size_t)v];
+		view.scale_modifier = scale_modifier;
+		view.sh_degree = degree;
+		view.sh_coeffs = (g.shs != nullptr) ? (int)sh.size(1) : 0;
+		view.prefiltered = prefiltered;
+		view.debug = debug;
+		view.bg = bg;
+		view.viewmatrix = vm + 16 * (size_t)v;
+		view.projmatrix = pm + 16 * (size_t)v;
+		view.campos = cp ? cp + 3 * (size_t)v : nullptr;
+	}
+	brs_fwd_options opt{};
+	opt.mode = mode;
+	long long R = 0;
+	int st = brs_forward_views(views.data(), n, &g, out_color.data_ptr<float>(), out_depth.data_ptr<float>(),
+	                           P ? radii.data_ptr<int>() : nullptr, alloc_cb, &ctx, &R, &opt, current_stream());
+	check_status(st, "rasterize_gaussians_views");
+	return std::make_tuple((int64_t)R, out_color, out_depth, radii);
+}
+
 namespace {
 
 // Shared body of the two backward bindings: tensors -> C structs -> brs_backward with `grads`.
@@ -723,6 +799,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	// the forward blocks once on the device (instance count); it touches no Python object, so it runs
 	// without the GIL and several host threads can drive one CUDA stream each (render_views)
 	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA, pybind11::call_guard<pybind11::gil_scoped_release>());
+	m.def("rasterize_gaussians_views", &RasterizeGaussiansViewsCUDA, pybind11::arg("bg"), pybind11::arg("means3D"),
+	      pybind11::arg("colors"), pybind11::arg("opacity"), pybind11::arg("scales"), pybind11::arg("rotations"),
+	      pybind11::arg("scale_modifier"), pybind11::arg("cov3D_precomp"), pybind11::arg("viewmatrices"),
+	      pybind11::arg("projmatrices"), pybind11::arg("tan_fovx"), pybind11::arg("tan_fovy"), pybind11::arg("image_height"),
+	      pybind11::arg("image_width"), pybind11::arg("sh"), pybind11::arg("degree"), pybind11::arg("camposes"),
+	      pybind11::arg("prefiltered"), pybind11::arg("debug"), pybind11::arg("mode") = (int)BRS_FWD_AUTO);
 	m.def("rasterize_gaussians_ex", &RasterizeGaussiansExCUDA, pybind11::arg("bg"), pybind11::arg("means3D"), pybind11::arg("colors"),
 	      pybind11::arg("opacity"), pybind11::arg("scales"), pybind11::arg("rotations"), pybind11::arg("scale_modifier"),
 	      pybind11::arg("cov3D_precomp"), pybind11::arg("viewmatrix"), pybind11::arg("projmatrix"), pybind11::arg("tan_fovx"),

@@ -252,7 +252,7 @@ def bind(_C) -> SimpleNamespace:
                 return radii, idx[: int(count.item())]
 
     def render_views(raster_settings_list, means3D, opacities, shs=None, colors_precomp=None, scales=None,
-                     rotations=None, cov3D_precomp=None, streams=4, keep_radii=False, host_threads=True):
+                     rotations=None, cov3D_precomp=None, streams=4, keep_radii=False, host_threads=True, stack=0):
         """Forward-only render of one Gaussian set from a list of cameras (BloomScene's render_video loop,
         reference bloomscene.py:191-204, one `GaussianRasterizer` call per frame there).  Extension: no
         autograd graph, no saved state, and on a GPU the views are dealt onto `streams` CUDA streams so that
@@ -261,7 +261,13 @@ def bind(_C) -> SimpleNamespace:
         forward releases the GIL).  Returns (color [B,3,H,W], depth [B,1,H,W], radii list or None); every view's
         result is bit-identical to a single `GaussianRasterizer` call with the same settings.  The call returns
         after ONE host synchronisation for the whole batch (the reference waits once per frame,
-        rasterizer_impl.cu:282), plus one for the first frame of a (P, W, H) shape it has never seen."""
+        rasterizer_impl.cu:282), plus one for the first frame of a (P, W, H) shape it has never seen.
+
+        `stack` > 1: consecutive views are rendered `stack` at a time as ONE pipeline (`brs_forward_views`): one
+        preprocess launch per view into a shared instance space, then one depth sort, one emission / coarse sort /
+        fine binning and one blend launch for the whole stack, at most one host wait per stack; the stacks are
+        dealt onto `streams` lanes (streams=1: everything on the caller's stream).  Same bits as the per-view path.  Views of a stack must share background, scale modifier and flags
+        (a run of views that does not is cut into shorter stacks)."""
         views = list(raster_settings_list)
         if (shs is None) == (colors_precomp is None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
@@ -300,6 +306,56 @@ def bind(_C) -> SimpleNamespace:
             depth[j].copy_(out[2])
             if keep_radii:
                 radii[j] = out[3]
+
+        if int(stack) > 1 and hasattr(_C, "rasterize_gaussians_views") and dev.type == "cuda" and B > 0:
+            same = lambda a, b: (a.bg.data_ptr() == b.bg.data_ptr() and a.scale_modifier == b.scale_modifier and
+                                 a.sh_degree == b.sh_degree and a.prefiltered == b.prefiltered and a.debug == b.debug)
+            groups, j = [], 0
+            while j < B:
+                n = 1
+                while n < int(stack) and j + n < B and same(views[j], views[j + n]):
+                    n += 1
+                groups.append((j, n))
+                j += n
+            for rs in views:
+                if (rs.image_height, rs.image_width) != (H, W):
+                    raise Exception('render_views: all views of a batch must share one resolution')
+
+            def one_stack(j, n):
+                grp = views[j:j + n]
+                rs = grp[0]
+                vm = torch.stack([v.viewmatrix for v in grp])
+                pm = torch.stack([v.projmatrix for v in grp])
+                cps = torch.stack([v.campos for v in grp])
+                _, c, d, r = _C.rasterize_gaussians_views(
+                    rs.bg, m3, cp_, op, sc_, ro_, rs.scale_modifier, cv_, vm, pm, [float(v.tanfovx) for v in grp],
+                    [float(v.tanfovy) for v in grp], H, W, sh_, rs.sh_degree, cps, rs.prefiltered, rs.debug)
+                color[j:j + n].copy_(c)
+                depth[j:j + n].copy_(d)
+                if keep_radii:
+                    for q in range(n):
+                        radii[j + q] = r[q]
+                return r
+
+            with torch.no_grad():
+                n_lanes = max(1, min(int(streams), len(groups)))
+                if n_lanes == 1:
+                    for j, n in groups:
+                        one_stack(j, n)
+                else:
+                    # stacks are dealt onto lanes: one stack's preprocess / sort / binning under another's blend
+                    cur = torch.cuda.current_stream(dev)
+                    lanes = lane_streams(dev, n_lanes)
+                    for st in lanes:
+                        st.wait_stream(cur)
+                    for k, (j, n) in enumerate(groups):
+                        with torch.cuda.stream(lanes[k % n_lanes]):
+                            r = one_stack(j, n)
+                            if keep_radii:
+                                r.record_stream(cur)
+                    for st in lanes:
+                        cur.wait_stream(st)
+            return color, depth, radii
 
         with torch.no_grad():
             n_lanes = max(1, min(int(streams), B)) if dev.type == "cuda" else 1

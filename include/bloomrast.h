@@ -172,6 +172,21 @@ int brs_forward_ex(const brs_view* view, const brs_gaussians* g,
                    float* out_color, float* out_depth, int* radii,
                    brs_alloc_fn alloc, void* alloc_ctx,
                    brs_fwd_state* state, const brs_fwd_options* opt, brs_stream stream);
+/* Extension: forward-only render of n_views views of ONE set of Gaussians as one pipeline — the
+ * batched form of the loops the reference's callers run one blocking view at a time (bloomscene.py:191-204,
+ * gaussian_renderer/__init__.py:211-291).  The views' preprocess launches write into one instance space
+ * (instance v * P + i, tile rectangle shifted down by v * grid_y rows), then ONE depth sort, ONE emission /
+ * coarse sort / fine binning and ONE blend launch serve all views: per-tile order is (depth bits, Gaussian id)
+ * exactly as in n_views separate forwards, so every output is bit-identical to them.
+ * All views share image size, sh_degree / sh_coeffs and debug; the background of views[0] is used; tanfov,
+ * matrices, campos, scale_modifier and prefiltered are per view.  out_color [n,3,H,W], out_depth [n,1,H,W],
+ * radii [n,P].  Nothing is kept for a backward.  *num_rendered (optional) = the instances of all views together
+ * (-1 after a DEFERRED forward).  opt as in brs_forward_ex (NULL = BRS_FWD_AUTO: at most one host wait per STACK).
+ * Limits: n_views * P < 2^31, n_views * ceil(H / 16) < 65536. */
+int brs_forward_views(const brs_view* views, int n_views, const brs_gaussians* g,
+                      float* out_color, float* out_depth, int* radii,
+                      brs_alloc_fn alloc, void* alloc_ctx, long long* num_rendered,
+                      const brs_fwd_options* opt, brs_stream stream);
 /* Feeds the counts of a DEFERRED forward's report back into the high-water marks of its shape. */
 void brs_note_counts(int P, int image_width, int image_height, const uint32_t* report);
 /* High-water marks of a shape on the current device: returns 1 and fills out[3] = {R, R1, depth-key bits} if a

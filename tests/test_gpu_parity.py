@@ -447,6 +447,35 @@ def test_render_views_multi_stream_is_bit_identical_to_single_calls():
     assert (radii[0] > 0).sum() > 100
 
 
+@pytest.mark.parametrize("case", [("sh3", 60000, 320, 192, 9, 4), ("precomp", 30000, 200, 120, 7, 8),
+                                  ("sh1", 5000, 130, 70, 5, 2), ("precomp", 200000, 512, 512, 6, 3)],
+                         ids=["sh3_320x192_stack4", "precomp_200x120_stack8", "sh1_130x70_stack2", "precomp_512_stack3"])
+def test_render_views_stacked_pipeline_is_bit_identical_to_single_calls(case):
+    """brs_forward_views: a stack of views as ONE pipeline (one depth sort, one binning chain, one blend launch over
+    views * tiles) against one call per view — colour, depth and radii bit for bit.  Ragged image heights (192, 120, 70
+    are not multiples of the 128-pixel supertile; 120 and 70 not of the 16-pixel tile), stacks that do not divide the
+    number of views, and repeated calls (EXACT first, optimistic afterwards)."""
+    color_kind, P, W, H, B, stack = case
+    api = pl.ours()
+    dev = torch.device("cuda:0")
+    scene = synthetic.make_scene(P, "band", color_kind, -4.6, seed=11).to(dev)
+    cams = [synthetic.yaw_camera(W, H, 0.35 * k).to(dev) for k in range(B)]
+    bg = torch.tensor([0.3, 0.2, 0.1], device=dev)
+    settings = [synthetic.raster_settings(c, scene.sh_degree, bg, api.GaussianRasterizationSettings) for c in cams]
+    kw = dict(shs=scene.shs, colors_precomp=scene.colors_precomp, scales=scene.scales, rotations=scene.rotations)
+    for rep in range(2):
+        color, depth, radii = api.render_views(settings, scene.means3D, scene.opacities, keep_radii=True, stack=stack,
+                                               streams=1 + rep, **kw)  # one stream, then stacks dealt onto two lanes
+        torch.cuda.synchronize()
+        assert color.shape == (B, 3, H, W) and depth.shape == (B, 1, H, W)
+        with torch.no_grad():
+            for k, rs in enumerate(settings):
+                c, r, d = api.GaussianRasterizer(rs)(scene.means3D, torch.zeros_like(scene.means3D), scene.opacities, **kw)
+                assert torch.equal(r, radii[k]), (rep, k)
+                assert torch.equal(c, color[k]) and torch.equal(d, depth[k]), (rep, k)
+    assert sum(int((r > 0).sum()) for r in radii) > 100
+
+
 @pytest.mark.parametrize("color", ["sh2", "precomp"])
 def test_opt_in_depth_gradient_vs_cpu_oracle(color):
     """Extension: with depth_gradient=True the depth image back-propagates through D / acc.

@@ -52,7 +52,20 @@ def render_batched(api, scene, cams, bg, streams=4, reps=3, host_threads=True):
     settings = [synthetic.raster_settings(cam, scene.sh_degree, bg, api.GaussianRasterizationSettings) for cam in cams]
     kw = dict(shs=scene.shs, colors_precomp=scene.colors_precomp, scales=scene.scales, rotations=scene.rotations, streams=streams,
               host_threads=host_threads)
-    api.render_views(settings[:streams], scene.means3D, scene.opacities, **kw)  # warm-up
+    api.render_views(settings, scene.means3D, scene.opacities, **kw)  # warm-up: one full pass
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = api.render_views(settings, scene.means3D, scene.opacities, **kw)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / (reps * len(cams)) * 1e3, out
+
+
+def render_stacked(api, scene, cams, bg, stack, reps=3, streams=1):
+    """The same frames `stack` views at a time as one pipeline on ONE stream (render_views(stack=...), brs_forward_views)."""
+    settings = [synthetic.raster_settings(cam, scene.sh_degree, bg, api.GaussianRasterizationSettings) for cam in cams]
+    kw = dict(shs=scene.shs, colors_precomp=scene.colors_precomp, scales=scene.scales, rotations=scene.rotations, stack=stack, streams=streams)
+    api.render_views(settings, scene.means3D, scene.opacities, **kw)  # warm-up: one full pass (EXACT first, then the high-water marks settle)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -65,6 +78,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="A,B,C,D")
     ap.add_argument("--views", type=int, default=24)
+    ap.add_argument("--stacks", default="4,8", help="stack sizes of the one-pipeline path (configs B, D)")
+    ap.add_argument("--no-ref", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     mine, ref = pl.ours(), pl.reference()
@@ -96,7 +111,16 @@ def main():
                                                   "last_frame_equal_to_loop": bool(torch.equal(outb[0][-1], out[0]))}
             ms_b1, _ = render_batched(mine, scene, cams, bg, host_threads=False)
             rec["ours_render_views_4_streams"]["fwd_ms_per_view_one_host_thread"] = round(ms_b1, 4)
-            if ref is not None:
+            rec["ours_render_views_stacked_one_stream"] = {}
+            for stack in [int(x) for x in a.stacks.split(",") if x]:
+                ms_s, outs = render_stacked(mine, scene, cams, bg, stack)
+                rec["ours_render_views_stacked_one_stream"][f"stack{stack}"] = {
+                    "fwd_ms_per_view": round(ms_s, 4), "equal_to_multi_stream": bool(torch.equal(outs[0], outb[0]) and torch.equal(outs[1], outb[1]))}
+                for lanes in (2, 3):
+                    ms_l, outl = render_stacked(mine, scene, cams, bg, stack, streams=lanes)
+                    rec["ours_render_views_stacked_one_stream"][f"stack{stack}"][f"fwd_ms_per_view_{lanes}_lanes"] = round(ms_l, 4)
+                    rec["ours_render_views_stacked_one_stream"][f"stack{stack}"]["lanes_equal"] = bool(torch.equal(outl[0], outb[0]))
+            if ref is not None and not a.no_ref:
                 render_loop(ref, scene, cams[:3], bg)
                 ms_r, _ = render_loop(ref, scene, cams, bg)
                 rec["reference_cuda"] = {"fwd_ms_per_view": round(ms_r, 4), "views_per_s": round(1e3 / ms_r, 1)}

@@ -724,23 +724,43 @@ int forward_impl(const brs_view* views, int n_views, const brs_gaussians* g, flo
 	const bool have_marks = lookup_marks(key, marks);
 	// SH rows: requested for all Gaussians up front when most of them were visible in the last views of this shape
 	pa.eager_sh = (have_marks && 2ull * marks.V > (unsigned long long)P_inst) ? 1 : 0;
-	for (int v = 0; v < n_views; v++) {
-		const brs_view* vw = views + v;
-		pa.scale_modifier = vw->scale_modifier;
-		pa.viewmatrix = vw->viewmatrix;
-		pa.projmatrix = vw->projmatrix;
-		pa.campos = vw->campos;
-		pa.tan_fovx = vw->tanfovx;
-		pa.tan_fovy = vw->tanfovy;
-		pa.focal_y = H / (2.0f * vw->tanfovy); // rasterizer_impl.cu:223-224
-		pa.focal_x = W / (2.0f * vw->tanfovx);
-		pa.prefiltered = vw->prefiltered;
-		pa.row_offset = (uint32_t)v * c.grid_y;
-		pa.radii = radii + (size_t)v * P;
-		pa.records = reinterpret_cast<float4*>(c.geom + c.gl.records) + 3 * (size_t)v * P;
-		pa.depth_key = reinterpret_cast<uint32_t*>(c.geom + c.gl.depth_key) + (size_t)v * P;
-		pa.rect = reinterpret_cast<uint2*>(c.geom + c.gl.rect) + (size_t)v * P;
+	pa.radii = radii;
+	pa.records = reinterpret_cast<float4*>(c.geom + c.gl.records);
+	pa.depth_key = reinterpret_cast<uint32_t*>(c.geom + c.gl.depth_key);
+	pa.rect = reinterpret_cast<uint2*>(c.geom + c.gl.rect);
+	if (n_views == 1) {
+		pa.scale_modifier = view->scale_modifier;
+		pa.viewmatrix = view->viewmatrix;
+		pa.projmatrix = view->projmatrix;
+		pa.campos = view->campos;
+		pa.tan_fovx = view->tanfovx;
+		pa.tan_fovy = view->tanfovy;
+		pa.focal_y = H / (2.0f * view->tanfovy); // rasterizer_impl.cu:223-224
+		pa.focal_x = W / (2.0f * view->tanfovx);
+		pa.prefiltered = view->prefiltered;
+		pa.row_offset = 0;
 		BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess(pa, stream), debug, stream);
+	} else {
+		// one launch per 16 views: blockIdx.y picks the view, its outputs go to instances [v * P, (v + 1) * P)
+		for (int v0 = 0; v0 < n_views; v0 += PreprocessViewTable::MAX_VIEWS) {
+			const int nv = n_views - v0 < PreprocessViewTable::MAX_VIEWS ? n_views - v0 : PreprocessViewTable::MAX_VIEWS;
+			PreprocessViewTable t{};
+			t.first_view = (uint32_t)v0;
+			for (int k = 0; k < nv; k++) {
+				const brs_view* vw = views + v0 + k;
+				PreprocessViewTable::Slot& sl = t.v[k];
+				sl.viewmatrix = vw->viewmatrix;
+				sl.projmatrix = vw->projmatrix;
+				sl.campos = vw->campos;
+				sl.tan_fovx = vw->tanfovx;
+				sl.tan_fovy = vw->tanfovy;
+				sl.focal_y = H / (2.0f * vw->tanfovy);
+				sl.focal_x = W / (2.0f * vw->tanfovx);
+				sl.scale_modifier = vw->scale_modifier;
+				sl.prefiltered = vw->prefiltered;
+			}
+			BRS_STAGE(BRS_STAGE_PREPROCESS, launch_preprocess_stack(pa, t, nv, stream), debug, stream);
+		}
 	}
 
 	// ---- deferred: the caller's capacities (or the high-water marks), no host wait at all ----

@@ -37,6 +37,20 @@ struct PreprocessArgs {
 	                       // max(depth bits) over visible, V = number of visible Gaussians
 };
 cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream);
+// Up to MAX_VIEWS views of a stack in one launch: the per-view fields of PreprocessArgs come from the table,
+// view k of the launch is view first_view + k of the stack (row offset, output slices).
+struct PreprocessViewTable {
+	static constexpr int MAX_VIEWS = 16;
+	struct Slot {
+		const float* viewmatrix;
+		const float* projmatrix;
+		const float* campos;
+		float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
+		int prefiltered;
+	} v[MAX_VIEWS];
+	uint32_t first_view;
+};
+cudaError_t launch_preprocess_stack(const PreprocessArgs& a, const PreprocessViewTable& t, int n_views, cudaStream_t stream);
 
 struct FilterArgs {
 	int P;

@@ -200,7 +200,7 @@ __device__ __forceinline__ void stage_camera(float* s_cam, const float* view, co
 //   the visible Gaussians are requested, after the geometry phase.  The host picks EAGER when the last views
 //   of this shape had most Gaussians visible (the rows of culled Gaussians are wasted traffic).
 template <bool VEC, bool EAGER>
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs a)
+__device__ __forceinline__ void preprocess_body(const PreprocessArgs& a)
 {
 	extern __shared__ float4 s_dyn[]; // SH staging (only when a.shs != nullptr)
 	__shared__ float s_cam[36];
@@ -361,6 +361,33 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs 
 	}
 }
 
+// One view, or a stack of views in ONE launch (brs_forward_views): blockIdx.y picks the view; its camera, its
+// place in the stack (row offset) and its slice of the instance-indexed outputs come from the view table in
+// parameter space.  The Gaussians' inputs are read once per view, the later views' reads hitting L2.
+// A single view runs the same kernel with a one-entry table, so a stacked forward and per-view forwards execute
+// the same instructions (two separately compiled copies of the SH evaluation differed in the last bit).
+template <bool VEC, bool EAGER>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessArgs a, PreprocessViewTable t)
+{
+	const PreprocessViewTable::Slot& v = t.v[blockIdx.y];
+	const size_t first = (size_t)(t.first_view + blockIdx.y) * (size_t)a.P;
+	a.viewmatrix = v.viewmatrix;
+	a.projmatrix = v.projmatrix;
+	a.campos = v.campos;
+	a.tan_fovx = v.tan_fovx;
+	a.tan_fovy = v.tan_fovy;
+	a.focal_x = v.focal_x;
+	a.focal_y = v.focal_y;
+	a.scale_modifier = v.scale_modifier;
+	a.prefiltered = v.prefiltered;
+	a.row_offset += (t.first_view + blockIdx.y) * a.grid_y;
+	a.radii += first;
+	a.records += 3 * first;
+	a.depth_key += first;
+	a.rect += first;
+	preprocess_body<VEC, EAGER>(a);
+}
+
 // ---- K10 ----------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) filter_kernel(FilterArgs a)
@@ -480,9 +507,27 @@ __global__ void __launch_bounds__(256)
 
 cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream)
 {
-	if (a.P <= 0)
+	PreprocessViewTable t{};
+	PreprocessViewTable::Slot& s = t.v[0];
+	s.viewmatrix = a.viewmatrix;
+	s.projmatrix = a.projmatrix;
+	s.campos = a.campos;
+	s.tan_fovx = a.tan_fovx;
+	s.tan_fovy = a.tan_fovy;
+	s.focal_x = a.focal_x;
+	s.focal_y = a.focal_y;
+	s.scale_modifier = a.scale_modifier;
+	s.prefiltered = a.prefiltered;
+	return launch_preprocess_stack(a, t, 1, stream);
+}
+
+cudaError_t launch_preprocess_stack(const PreprocessArgs& a, const PreprocessViewTable& t, int n_views, cudaStream_t stream)
+{
+	if (a.P <= 0 || n_views <= 0)
 		return cudaSuccess;
-	const int blocks = (a.P + PRE_THREADS - 1) / PRE_THREADS;
+	if (n_views > PreprocessViewTable::MAX_VIEWS)
+		return cudaErrorInvalidValue;
+	const dim3 grid((a.P + PRE_THREADS - 1) / PRE_THREADS, n_views, 1);
 	size_t smem = 0;
 	bool vec = false;
 	if (a.shs != nullptr) {
@@ -490,11 +535,11 @@ cudaError_t launch_preprocess(const PreprocessArgs& a, cudaStream_t stream)
 		smem = vec ? (size_t)(PRE_THREADS / 2) * SH_PAIR_PITCH * sizeof(float4) : (size_t)PRE_THREADS * ((3 * a.M) | 1) * sizeof(float);
 	}
 	if (vec && a.eager_sh)
-		preprocess_kernel<true, true><<<blocks, PRE_THREADS, smem, stream>>>(a);
+		preprocess_kernel<true, true><<<grid, PRE_THREADS, smem, stream>>>(a, t);
 	else if (vec)
-		preprocess_kernel<true, false><<<blocks, PRE_THREADS, smem, stream>>>(a);
+		preprocess_kernel<true, false><<<grid, PRE_THREADS, smem, stream>>>(a, t);
 	else
-		preprocess_kernel<false, false><<<blocks, PRE_THREADS, smem, stream>>>(a);
+		preprocess_kernel<false, false><<<grid, PRE_THREADS, smem, stream>>>(a, t);
 	count_launch();
 	return cudaGetLastError();
 }

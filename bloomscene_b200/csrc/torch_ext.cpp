@@ -191,7 +191,8 @@ RasterizeGaussiansViewsCUDA(const torch::Tensor& background, const torch::Tensor
                             const torch::Tensor& projmatrices, const std::vector<double>& tan_fovx,
                             const std::vector<double>& tan_fovy, const int image_height, const int image_width,
                             const torch::Tensor& sh, const int degree, const torch::Tensor& camposes, const bool prefiltered,
-                            const bool debug, const int mode)
+                            const bool debug, const int mode, const c10::optional<torch::Tensor>& color_out,
+                            const c10::optional<torch::Tensor>& depth_out)
 {
 	TORCH_CHECK(means3D.ndimension() == 2 && means3D.size(1) == 3, "means3D must have dimensions (num_points, 3)");
 	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
@@ -206,8 +207,17 @@ RasterizeGaussiansViewsCUDA(const torch::Tensor& background, const torch::Tensor
 
 	const int P = means3D.size(0), H = image_height, W = image_width;
 	auto float_opts = means3D.options().dtype(torch::kFloat32);
-	torch::Tensor out_color = torch::empty({n, 3, H, W}, float_opts);
-	torch::Tensor out_depth = torch::empty({n, 1, H, W}, float_opts);
+	// the caller may hand in (a slice of) its own output stacks: written in place, no copy afterwards
+	auto take = [&](const c10::optional<torch::Tensor>& t, int64_t ch, const char* name) {
+		if (!t.has_value() || !t->defined())
+			return torch::empty({n, ch, H, W}, float_opts);
+		TORCH_CHECK(t->is_cuda() && t->device() == means3D.device() && t->scalar_type() == torch::kFloat32 && t->is_contiguous() &&
+		                t->numel() == (int64_t)n * ch * H * W,
+		            name, " must be a contiguous float32 CUDA tensor of views x ", ch, " x H x W elements");
+		return *t;
+	};
+	torch::Tensor out_color = take(color_out, 3, "color_out");
+	torch::Tensor out_depth = take(depth_out, 1, "depth_out");
 	torch::Tensor radii = torch::empty({n, P}, means3D.options().dtype(torch::kInt32));
 
 	AllocCtx ctx;
@@ -804,7 +814,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	      pybind11::arg("scale_modifier"), pybind11::arg("cov3D_precomp"), pybind11::arg("viewmatrices"),
 	      pybind11::arg("projmatrices"), pybind11::arg("tan_fovx"), pybind11::arg("tan_fovy"), pybind11::arg("image_height"),
 	      pybind11::arg("image_width"), pybind11::arg("sh"), pybind11::arg("degree"), pybind11::arg("camposes"),
-	      pybind11::arg("prefiltered"), pybind11::arg("debug"), pybind11::arg("mode") = (int)BRS_FWD_AUTO);
+	      pybind11::arg("prefiltered"), pybind11::arg("debug"), pybind11::arg("mode") = (int)BRS_FWD_AUTO,
+	      pybind11::arg("color_out") = c10::nullopt, pybind11::arg("depth_out") = c10::nullopt);
 	m.def("rasterize_gaussians_ex", &RasterizeGaussiansExCUDA, pybind11::arg("bg"), pybind11::arg("means3D"), pybind11::arg("colors"),
 	      pybind11::arg("opacity"), pybind11::arg("scales"), pybind11::arg("rotations"), pybind11::arg("scale_modifier"),
 	      pybind11::arg("cov3D_precomp"), pybind11::arg("viewmatrix"), pybind11::arg("projmatrix"), pybind11::arg("tan_fovx"),

@@ -327,11 +327,10 @@ def bind(_C) -> SimpleNamespace:
                 vm = torch.stack([v.viewmatrix for v in grp])
                 pm = torch.stack([v.projmatrix for v in grp])
                 cps = torch.stack([v.campos for v in grp])
-                _, c, d, r = _C.rasterize_gaussians_views(
+                _, _, _, r = _C.rasterize_gaussians_views(
                     rs.bg, m3, cp_, op, sc_, ro_, rs.scale_modifier, cv_, vm, pm, [float(v.tanfovx) for v in grp],
-                    [float(v.tanfovy) for v in grp], H, W, sh_, rs.sh_degree, cps, rs.prefiltered, rs.debug)
-                color[j:j + n].copy_(c)
-                depth[j:j + n].copy_(d)
+                    [float(v.tanfovy) for v in grp], H, W, sh_, rs.sh_degree, cps, rs.prefiltered, rs.debug,
+                    color_out=color[j:j + n], depth_out=depth[j:j + n])  # written in place
                 if keep_radii:
                     for q in range(n):
                         radii[j + q] = r[q]

@@ -47,31 +47,34 @@ def render_loop(api, scene, cams, bg, reps=1):
     return dt / (reps * len(cams)) * 1e3, out
 
 
-def render_batched(api, scene, cams, bg, streams=4, reps=3, host_threads=True):
+def _median_pass(fn, reps, n_views):
+    """ms per view of one pass over the view list: median over `reps` passes, each synchronised on both sides (a single
+    pass can catch an allocator growth or a capacity re-run of a shape's first views)."""
+    times, out = [], None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) / n_views * 1e3)
+    return sorted(times)[len(times) // 2], out
+
+
+def render_batched(api, scene, cams, bg, streams=4, reps=5, host_threads=True):
     """The same frames through the forward-only batch entry point (render_views: views dealt onto CUDA streams)."""
     settings = [synthetic.raster_settings(cam, scene.sh_degree, bg, api.GaussianRasterizationSettings) for cam in cams]
     kw = dict(shs=scene.shs, colors_precomp=scene.colors_precomp, scales=scene.scales, rotations=scene.rotations, streams=streams,
               host_threads=host_threads)
     api.render_views(settings, scene.means3D, scene.opacities, **kw)  # warm-up: one full pass
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        out = api.render_views(settings, scene.means3D, scene.opacities, **kw)
-    torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / (reps * len(cams)) * 1e3, out
+    return _median_pass(lambda: api.render_views(settings, scene.means3D, scene.opacities, **kw), reps, len(cams))
 
 
-def render_stacked(api, scene, cams, bg, stack, reps=3, streams=1):
+def render_stacked(api, scene, cams, bg, stack, reps=5, streams=1):
     """The same frames `stack` views at a time as one pipeline on ONE stream (render_views(stack=...), brs_forward_views)."""
     settings = [synthetic.raster_settings(cam, scene.sh_degree, bg, api.GaussianRasterizationSettings) for cam in cams]
     kw = dict(shs=scene.shs, colors_precomp=scene.colors_precomp, scales=scene.scales, rotations=scene.rotations, stack=stack, streams=streams)
     api.render_views(settings, scene.means3D, scene.opacities, **kw)  # warm-up: one full pass (EXACT first, then the high-water marks settle)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        out = api.render_views(settings, scene.means3D, scene.opacities, **kw)
-    torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / (reps * len(cams)) * 1e3, out
+    return _median_pass(lambda: api.render_views(settings, scene.means3D, scene.opacities, **kw), reps, len(cams))
 
 
 def main():

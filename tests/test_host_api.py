@@ -56,6 +56,46 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     assert lib.brs_sort_pairs_u32(None, None, None, None, 8, 0, 33, None, None) == -1
 
 
+class _View(C.Structure):
+    _fields_ = [("image_width", C.c_int), ("image_height", C.c_int), ("tanfovx", C.c_float), ("tanfovy", C.c_float),
+                ("scale_modifier", C.c_float), ("sh_degree", C.c_int), ("sh_coeffs", C.c_int), ("prefiltered", C.c_int),
+                ("debug", C.c_int), ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+                ("campos", C.c_void_p)]
+
+
+class _Gaussians(C.Structure):
+    _fields_ = [("P", C.c_int)] + [(n, C.c_void_p) for n in ("means3D", "opacities", "shs", "colors_precomp", "scales",
+                                                             "rotations", "cov3D_precomp")]
+
+
+def test_forward_views_validates_the_stack_without_touching_the_gpu():
+    """brs_forward_views: the views of a stack must agree on image size and SH layout; counts must fit 32-bit instance ids
+    and 16-bit stacked tile rows.  All rejected before any CUDA call (the pointers are fake)."""
+    lib = _lib()
+    ALLOC = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
+    alloc = ALLOC(lambda ctx, which, n: None)
+    fake = 0x1000
+
+    def view(W=64, H=48, deg=0):
+        return _View(W, H, 0.5, 0.5, 1.0, deg, 0, 0, 0, fake, fake, fake, fake)
+
+    def call(views, g, n=None):
+        arr = (_View * len(views))(*views)
+        return lib.brs_forward_views(arr, len(views) if n is None else n, C.byref(g), C.c_void_p(fake), C.c_void_p(fake),
+                                     C.c_void_p(fake), alloc, None, None, None, None)
+
+    g = _Gaussians(100, fake, fake, None, fake, fake, fake, None)
+    assert lib.brs_forward_views(None, 2, C.byref(g), None, None, None, alloc, None, None, None, None) == -1
+    assert call([view()], g, n=0) == -1
+    assert call([view(), view(W=80)], g) == -1            # different image sizes in one stack
+    assert call([view(), view(deg=1)], g) == -1           # different SH degree
+    both = _Gaussians(100, fake, fake, fake, fake, fake, fake, None)
+    assert call([view(), view()], both) == -1             # shs AND colors_precomp (reference raises for it)
+    big = _Gaussians(2**30, fake, fake, None, fake, fake, fake, None)
+    assert call([view(), view(), view()], big) == -4      # 3 * 2^30 instances do not fit 32-bit ids: BRS_ERR_UNSUPPORTED
+    assert call([view(H=16 * 40000), view(H=16 * 40000)], g) == -4   # 80 000 stacked tile rows > 16 bits
+
+
 def test_state_layout_is_consistent():
     from bloomscene_b200 import _C
 
@@ -85,6 +125,8 @@ def test_python_surface_matches_reference_package():
     # the four reference binding names (ext.cpp:15-20), including the reference's own spelling
     for fn in ("rasterize_gaussians", "rasterize_gaussians_backward", "rasterize_aussians_filter", "mark_visible"):
         assert hasattr(ddgr._C, fn)
+    # extensions stay keyword-only additions: the batch entry point and its stacked pipeline
+    assert "stack" in inspect.signature(ddgr.render_views).parameters and hasattr(ddgr._C, "rasterize_gaussians_views")
 
 
 def _settings(S, W=32, H=32):

@@ -1,2 +1,4 @@
-timeout 1500 python tools/bench_configs.py --configs A,B,C,D --views 120 --stacks 8,16 > gpurun_out/r2F_configs.jsonl 2> gpurun_out/r2F_configs.err
-cut -c1-2200 gpurun_out/r2F_configs.jsonl; tail -3 gpurun_out/r2F_configs.err
+for t in memcheck racecheck synccheck initcheck; do
+  echo "== $t"; timeout 1200 compute-sanitizer --tool $t python tools/sanitize_small.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|error|hazard|step loss|modes" | sort | uniq -c | head -12
+done > gpurun_out/r2G_sanitizer.txt 2>&1
+cat gpurun_out/r2G_sanitizer.txt

@@ -36,6 +36,12 @@ for (P, color, W, H, mu) in [(3000, "sh3", 160, 96, -3.2), (1500, "precomp", 70,
     ((c_img * Wc).sum() + (d_img * Wd).sum()).backward()
     frames = api.render_views(settings, scene.means3D, scene.opacities, scales=scene.scales, rotations=scene.rotations, **col)
     torch.cuda.synchronize()
+    # the same frames as ONE stacked pipeline (brs_forward_views), twice: EXACT, then optimistic; then on two lanes
+    for lanes in (1, 1, 2):
+        stacked = api.render_views(settings, scene.means3D, scene.opacities, scales=scene.scales, rotations=scene.rotations,
+                                   stack=3, streams=lanes, **col)
+        torch.cuda.synchronize()
+        assert torch.equal(stacked[0], frames[0]) and torch.equal(stacked[1], frames[1])
     print("depth-grad", float(leaves["means3D"].grad.abs().sum()), "frames", float(frames[0].sum()))
     # forward modes: optimistic with stale marks (overflow -> re-run), deferred with far too small capacities
     _C = api._C

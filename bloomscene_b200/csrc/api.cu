@@ -334,16 +334,16 @@ size_t brs_image_bytes(int W, int H) { return image_layout(W, H).total; }
 size_t brs_sort_scratch_bytes(int n) { return sort_scratch_bytes(n < 0 ? 0 : (size_t)n); }
 
 // Scratch of one forward with the given capacities: [zeroed: depth sort | instance levels][plain: both].
-static size_t forward_scratch_bytes(size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y, int depth_passes)
+static size_t forward_scratch_bytes(size_t P, size_t V_cap, size_t R1_cap, uint32_t grid_x, uint32_t grid_y, int depth_passes)
 {
-	return depth_zero_bytes(P, depth_passes) + inst_zero_bytes(P, R1_cap, grid_x, grid_y) + depth_plain_bytes(P) +
+	return depth_zero_bytes(P, V_cap, depth_passes) + inst_zero_bytes(P, R1_cap, grid_x, grid_y) + depth_plain_bytes(P) +
 	       inst_plain_bytes(P, R1_cap, grid_x, grid_y);
 }
 size_t brs_forward_scratch_bytes(int P, int R, int W, int H)
 {
 	const uint32_t gx = W > 0 ? (W + TILE_X - 1) / TILE_X : 0, gy = H > 0 ? (H + TILE_Y - 1) / TILE_Y : 0;
 	// R1 (supertile instances) never exceeds R (tile instances)
-	return forward_scratch_bytes(P < 0 ? 0 : P, R < 0 ? 0 : R, gx, gy, 4);
+	return forward_scratch_bytes(P < 0 ? 0 : P, P < 0 ? 0 : P, R < 0 ? 0 : R, gx, gy, 4);
 }
 size_t brs_backward_scratch_bytes(int P) { return align_up(sizeof(float) * ACCUM_STRIDE * (P < 0 ? 0 : (size_t)P), 256); }
 
@@ -485,6 +485,7 @@ void raise_marks(const MarksKey& k, uint32_t R, uint32_t R1, uint32_t key_bits, 
 
 struct Caps {
 	uint32_t R_cap, R1_cap;
+	uint32_t V_cap = 0xffffffffu; // visible Gaussians (all of them unless known better)
 	int depth_passes;
 };
 int passes_for_bits(uint32_t key_bits)
@@ -497,6 +498,7 @@ Caps caps_from_marks(const Marks& m)
 	Caps c;
 	c.R_cap = m.R + m.R / 4 + 4096;
 	c.R1_cap = m.R1 + m.R1 / 4 + 4096;
+	c.V_cap = m.V + m.V / 4 + 4096;
 	c.depth_passes = passes_for_bits(m.key_bits + 1);
 	return c;
 }
@@ -540,6 +542,7 @@ int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* r
 	pl.P = (uint32_t)P_inst;
 	pl.R1_cap = caps.R1_cap;
 	pl.R_cap = caps.R_cap;
+	pl.V_cap = caps.V_cap < P_inst ? caps.V_cap : (uint32_t)P_inst;
 	pl.grid_x = c.grid_x;
 	pl.grid_y = rows;
 	pl.ns_x = supertiles(c.grid_x);
@@ -555,14 +558,14 @@ int enqueue_binning_and_blend(const ForwardCtx& c, const Caps& caps, uint32_t* r
 
 	const bool have_grid = c.grid_x * rows > 0;
 	if (have_grid) {
-		const size_t dz = depth_zero_bytes(P_inst, caps.depth_passes), iz = inst_zero_bytes(P_inst, caps.R1_cap, c.grid_x, rows);
+		const size_t dz = depth_zero_bytes(P_inst, caps.V_cap, caps.depth_passes), iz = inst_zero_bytes(P_inst, caps.R1_cap, c.grid_x, rows);
 		const size_t dp = depth_plain_bytes(P_inst);
 		char* scratch = static_cast<char*>(
-		    c.alloc(c.alloc_ctx, BRS_BUF_SCRATCH, forward_scratch_bytes(P_inst, caps.R1_cap, c.grid_x, rows, caps.depth_passes)));
+		    c.alloc(c.alloc_ctx, BRS_BUF_SCRATCH, forward_scratch_bytes(P_inst, caps.V_cap, caps.R1_cap, c.grid_x, rows, caps.depth_passes)));
 		if (scratch == nullptr)
 			return BRS_ERR_ALLOC;
 		BRS_CUDA(cudaMemsetAsync(scratch, 0, dz + iz, stream)); // tickets, histograms, look-back status words
-		pl.d = carve_depth_scratch(scratch, scratch + dz + iz, P_inst, caps.depth_passes);
+		pl.d = carve_depth_scratch(scratch, scratch + dz + iz, P_inst, caps.V_cap, caps.depth_passes);
 		pl.i = carve_inst_scratch(scratch + dz, scratch + dz + iz + dp, P_inst, caps.R1_cap, c.grid_x, rows);
 
 		BRS_STAGE(BRS_STAGE_DEPTH_SORT, launch_depth_sort_begin(pl, caps.depth_passes, stream), debug, stream);
@@ -766,6 +769,8 @@ int forward_impl(const brs_view* views, int n_views, const brs_gaussians* g, flo
 	// ---- deferred: the caller's capacities (or the high-water marks), no host wait at all ----
 	if (mode == BRS_FWD_DEFERRED) {
 		Caps caps = caps_from_marks(marks); // zero marks -> the 4096-instance floor
+		if (!have_marks)
+			caps.V_cap = 0xffffffffu; // the caller's capacities speak for R and R1 only
 		if (opt->R_cap > 0)
 			caps.R_cap = (uint32_t)opt->R_cap;
 		if (opt->R1_cap > 0)
@@ -822,6 +827,7 @@ int forward_impl(const brs_view* views, int n_views, const brs_gaussians* g, flo
 	}
 	caps.R_cap = R;
 	caps.R1_cap = R1;
+	caps.V_cap = V;
 	caps.depth_passes = passes_for_bits(key_bits);
 	state->num_rendered = (int)R;
 	raise_marks(key, R, R1, key_bits, V);

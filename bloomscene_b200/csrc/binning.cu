@@ -52,8 +52,7 @@ namespace {
 
 constexpr int OS_THREADS = 256;
 constexpr int OS_WARPS = OS_THREADS / 32;
-constexpr int OS_ITEMS = 16;
-constexpr int OS_TILE = OS_THREADS * OS_ITEMS; // 4096 pairs per tile
+constexpr int OS_ITEMS_MAX = 16; // keys per thread: 16 (4096-pair tiles) for big inputs, fewer for small ones, see sort_items()
 constexpr int RADIX = 256;
 
 constexpr uint32_t FLAG_LOCAL = 1u << 30; // tile-local count published
@@ -118,7 +117,7 @@ struct HistArgs {
 	int passes;
 	int shift[4], bits[4];
 	int drop;                // keys equal to DEPTH_KEY_CULLED do not take part
-	uint32_t R_cap, R1_cap;  // for the overflow word (depth sort only)
+	uint32_t R_cap, R1_cap, V_cap; // for the overflow word (depth sort only)
 	uint32_t* overflow_accum; // optional: the overflow bits are also OR-ed into this word
 	uint32_t* hist;          // [passes][RADIX], pre-zeroed
 };
@@ -151,6 +150,8 @@ __global__ void __launch_bounds__(OS_THREADS) radix_hist_kernel(HistArgs a)
 			flags |= 2u;
 		if ((int)nbits > planned)
 			flags |= 4u;
+		if (V > a.V_cap)
+			flags |= 8u;
 		a.hdr_out[HDR_OVERFLOW] = flags;
 		a.hdr_out[HDR_KEY_BITS] = nbits;
 		if (a.overflow_accum != nullptr && flags != 0u)
@@ -182,6 +183,8 @@ struct PassArgs {
 	uint32_t* vout;
 	uint32_t n;              // capacity
 	const uint32_t* n_ptr;   // actual count (nullptr: n)
+	uint32_t out_cap;        // entries of kout / vout: positions beyond it are dropped (only reachable after a capacity
+	                         // overflow, when the digit totals count keys the pass does not see)
 	const uint32_t* hdr;     // depth sort: bias from the header; nullptr: bias 0
 	int shift, bits;
 	int drop;
@@ -191,8 +194,10 @@ struct PassArgs {
 	uint32_t* ticket;        // pre-zeroed
 };
 
+template <int OS_ITEMS>
 __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(PassArgs a)
 {
+	constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
 	__shared__ uint32_t s_cnt[OS_WARPS][RADIX];
 	__shared__ uint32_t s_keys[OS_TILE];
 	__shared__ uint32_t s_vals[OS_TILE];
@@ -327,14 +332,44 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(PassArgs a)
 		if (j < kept) {
 			const uint32_t k = s_keys[j];
 			const uint32_t g = s_goff[((k - bias) >> a.shift) & mask] + j;
-			if (a.kout)
-				a.kout[g] = k;
-			a.vout[g] = s_vals[j];
+			if (g < a.out_cap) {
+				if (a.kout)
+					a.kout[g] = k;
+				a.vout[g] = s_vals[j];
+			}
 		}
 	}
 }
 
-inline uint32_t sort_tiles(size_t n) { return (uint32_t)((n + OS_TILE - 1) / OS_TILE); }
+// Keys per thread of a pass over (at most) n pairs.  A tile's work is a latency chain (ticket -> loads -> ranking ->
+// look-back -> scatter); with 4096-pair tiles an input of 100 K pairs is 25 CTAs on 148 SMs, each walking 16 keys per
+// thread through that chain.  Smaller tiles spread a small input over the SMs and shorten the chain; big inputs keep
+// the big tiles (fewer status words, fewer look-back steps per key).  Chosen from the CAPACITY, which the host knows
+// when it sizes the status arrays.
+inline int sort_items(size_t n)
+{
+	static const int forced = [] { const char* e = getenv("BRS_SORT_ITEMS"); return e ? atoi(e) : 0; }();
+	if (forced == 4 || forced == 8 || forced == 16)
+		return forced;
+	return n <= 128u * 1024u ? 4 : (n <= 384u * 1024u ? 8 : 16); // measured against CUB at 50 K ... 3 M pairs
+}
+inline uint32_t sort_tiles(size_t n)
+{
+	const size_t tile = (size_t)OS_THREADS * sort_items(n);
+	return (uint32_t)((n + tile - 1) / tile);
+}
+inline void launch_onesweep(const PassArgs& a, size_t capacity, cudaStream_t stream)
+{
+	const uint32_t tiles = sort_tiles(capacity);
+	if (tiles == 0)
+		return; // capacity 0 (nothing visible, known exactly): nothing to sort
+	count_launch();
+	switch (sort_items(capacity)) {
+	case 4: onesweep_kernel<4><<<tiles, OS_THREADS, 0, stream>>>(a); break;
+	case 8: onesweep_kernel<8><<<tiles, OS_THREADS, 0, stream>>>(a); break;
+	default: onesweep_kernel<16><<<tiles, OS_THREADS, 0, stream>>>(a); break;
+	}
+}
 
 // ---- fused scan + emission --------------------------------------------------------------------------
 
@@ -355,7 +390,9 @@ __device__ __forceinline__ uint2 coarsen_rect(uint2 r, uint32_t shift)
 struct EmitArgs {
 	const uint32_t* order;   // ids in depth order
 	const uint2* rect;
-	const uint32_t* hdr;     // V = hdr[HDR_V]
+	const uint32_t* hdr;     // V = min(hdr[HDR_V], V_cap)
+	uint32_t V_cap;          // entries of `order` the depth sort can have written
+	uint32_t P;              // ids are < P
 	uint32_t shift, ns_x, ns;
 	uint32_t* cell_keys;     // [R1_cap]
 	uint32_t* cell_ids;      // [R1_cap]
@@ -411,7 +448,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(EmitArgs a)
 			s_hist[i] = 0;
 	__syncthreads();
 	const uint32_t blk = s_bcast[0];
-	const uint32_t V = __ldg(a.hdr + HDR_V);
+	const uint32_t V = min(__ldg(a.hdr + HDR_V), a.V_cap); // beyond the capacity: the overflow word is raised, the caller re-runs
 	const uint32_t blocks = (V + EMIT_TILE - 1) / EMIT_TILE;
 	if (blk >= blocks) {
 		if (blocks == 0 && blk == 0)
@@ -429,7 +466,11 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(EmitArgs a)
 		uint2 r = make_uint2(0u, 0u);
 		if (s < V) {
 			id = __ldg(a.order + s);
-			r = coarsen_rect(__ldg(a.rect + id), a.shift);
+			// after a V_cap overflow the sort leaves unwritten slots in `order`: any value may sit there
+			if (id < a.P)
+				r = coarsen_rect(__ldg(a.rect + id), a.shift);
+			else
+				id = 0;
 		}
 		const uint32_t w = (r.x >> 16) - (r.x & 0xffffu);
 		const uint32_t hgt = (r.y >> 16) - (r.y & 0xffffu);
@@ -746,14 +787,16 @@ struct DepthCarve {
 	DepthScratch s;
 	size_t zero_bytes, plain_bytes;
 };
-DepthCarve carve_depth(void* zeroed, void* plain, size_t P, int passes)
+DepthCarve carve_depth(void* zeroed, void* plain, size_t P, size_t V_cap, int passes)
 {
 	DepthCarve c{};
-	const size_t tiles = sort_tiles(P);
+	// the first pass works on the P keys, the later ones on the (at most V_cap) visible ones it kept
+	const size_t tiles = sort_tiles(P), tiles_rest = sort_tiles(V_cap < P ? V_cap : P);
 	char* z = static_cast<char*>(zeroed);
 	c.s.ctl = carve<uint32_t>(z, DCTL_WORDS);
 	c.s.hist = carve<uint32_t>(z, 4 * RADIX);
-	c.s.status = carve<uint32_t>(z, (size_t)passes * tiles * RADIX);
+	c.s.status = carve<uint32_t>(z, (tiles + (size_t)(passes > 1 ? passes - 1 : 0) * tiles_rest) * RADIX);
+	c.s.tiles_rest = (uint32_t)tiles_rest;
 	c.zero_bytes = (size_t)(z - static_cast<char*>(zeroed));
 	char* p = static_cast<char*>(plain);
 	for (int i = 0; i < 2; i++) {
@@ -801,9 +844,12 @@ InstCarve carve_inst(void* zeroed, void* plain, size_t P, size_t R1_cap, uint32_
 }
 } // namespace
 
-size_t depth_zero_bytes(size_t P, int passes) { return carve_depth(nullptr, nullptr, P, passes).zero_bytes; }
-size_t depth_plain_bytes(size_t P) { return carve_depth(nullptr, nullptr, P, 1).plain_bytes; }
-DepthScratch carve_depth_scratch(void* zeroed, void* plain, size_t P, int passes) { return carve_depth(zeroed, plain, P, passes).s; }
+size_t depth_zero_bytes(size_t P, size_t V_cap, int passes) { return carve_depth(nullptr, nullptr, P, V_cap, passes).zero_bytes; }
+size_t depth_plain_bytes(size_t P) { return carve_depth(nullptr, nullptr, P, P, 1).plain_bytes; }
+DepthScratch carve_depth_scratch(void* zeroed, void* plain, size_t P, size_t V_cap, int passes)
+{
+	return carve_depth(zeroed, plain, P, V_cap, passes).s;
+}
 size_t inst_zero_bytes(size_t P, size_t R1_cap, uint32_t grid_x, uint32_t grid_y)
 {
 	return carve_inst(nullptr, nullptr, P, R1_cap, grid_x, grid_y).zero_bytes;
@@ -827,7 +873,8 @@ PassArgs depth_pass_args(const BinPlan& pl, int p)
 	a.vin = p == 0 ? nullptr : d.vals[(p - 1) & 1];
 	a.kout = last ? nullptr : d.keys[p & 1];
 	a.vout = last ? pl.order : d.vals[p & 1];
-	a.n = pl.P;
+	a.n = p == 0 ? pl.P : min(pl.P, pl.V_cap);
+	a.out_cap = pl.P;
 	a.n_ptr = p == 0 ? nullptr : pl.hdr + HDR_V; // the first pass drops the culled Gaussians
 	a.hdr = pl.hdr;
 	a.shift = 8 * p;
@@ -835,7 +882,7 @@ PassArgs depth_pass_args(const BinPlan& pl, int p)
 	a.drop = p == 0;
 	a.hist = d.hist + p * RADIX;
 	a.fold_n = 0;
-	a.status = d.status + (size_t)p * d.tiles * RADIX;
+	a.status = d.status + (p == 0 ? 0 : ((size_t)d.tiles + (size_t)(p - 1) * d.tiles_rest) * RADIX);
 	a.ticket = d.ctl + DCTL_TICKET + p;
 	return a;
 }
@@ -864,13 +911,13 @@ cudaError_t launch_depth_sort_begin(const BinPlan& pl, int planned_passes, cudaS
 	h.drop = 1;
 	h.R_cap = pl.R_cap;
 	h.R1_cap = pl.R1_cap;
+	h.V_cap = pl.V_cap;
 	h.overflow_accum = pl.overflow_accum;
 	h.hist = pl.d.hist;
 	const uint32_t hist_grid = (uint32_t)std::min<size_t>((pl.P + 2047) / 2048, 296);
 	radix_hist_kernel<<<hist_grid, OS_THREADS, 0, stream>>>(h);
 	count_launch();
-	onesweep_kernel<<<pl.d.tiles, OS_THREADS, 0, stream>>>(depth_pass_args(pl, 0));
-	count_launch();
+	launch_onesweep(depth_pass_args(pl, 0), pl.P, stream);
 	return cudaGetLastError();
 }
 
@@ -879,8 +926,7 @@ cudaError_t launch_depth_sort_rest(const BinPlan& pl, cudaStream_t stream)
 	if (pl.P == 0)
 		return cudaSuccess;
 	for (int p = 1; p < pl.depth_passes; p++) {
-		onesweep_kernel<<<pl.d.tiles, OS_THREADS, 0, stream>>>(depth_pass_args(pl, p));
-		count_launch();
+		launch_onesweep(depth_pass_args(pl, p), min(pl.P, pl.V_cap), stream);
 	}
 	return cudaGetLastError();
 }
@@ -894,6 +940,8 @@ cudaError_t launch_emit(const BinPlan& pl, cudaStream_t stream)
 	a.order = pl.order;
 	a.rect = pl.rect;
 	a.hdr = pl.hdr;
+	a.V_cap = min(pl.P, pl.V_cap);
+	a.P = pl.P;
 	a.shift = ST_SHIFT;
 	a.ns_x = pl.ns_x;
 	a.ns = pl.ns;
@@ -907,7 +955,7 @@ cudaError_t launch_emit(const BinPlan& pl, cudaStream_t stream)
 	a.coarse_ranges = b.coarse_ranges;
 	a.slice_base = b.slice_base;
 	a.n_instances = b.ctl + ICTL_N_INSTANCES;
-	const uint32_t blocks = (uint32_t)((pl.P + EMIT_TILE - 1) / EMIT_TILE);
+	const uint32_t blocks = max(1u, (uint32_t)((min(pl.P, pl.V_cap) + EMIT_TILE - 1) / EMIT_TILE)); // >= 1: an empty emission still writes the (empty) plan
 	emit_kernel<<<blocks, EMIT_THREADS, 0, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
@@ -934,6 +982,7 @@ cudaError_t launch_coarse_sort(const BinPlan& pl, cudaStream_t stream)
 		a.kout = last ? nullptr : b.tmp_keys;
 		a.vout = last ? b.coarse_list : b.tmp_ids;
 		a.n = pl.R1_cap;
+		a.out_cap = pl.R1_cap;
 		a.n_ptr = b.ctl + ICTL_N_INSTANCES;
 		a.hdr = nullptr;
 		a.shift = p == 0 ? 0 : lo_bits;
@@ -943,8 +992,7 @@ cudaError_t launch_coarse_sort(const BinPlan& pl, cudaStream_t stream)
 		a.fold_n = pl.ns;
 		a.status = b.coarse_status + (size_t)p * b.coarse_tiles * RADIX;
 		a.ticket = b.ctl + ICTL_COARSE_TICKET + p;
-		onesweep_kernel<<<b.coarse_tiles, OS_THREADS, 0, stream>>>(a);
-		count_launch();
+		launch_onesweep(a, pl.R1_cap, stream);
 	}
 	return cudaGetLastError();
 }
@@ -1041,13 +1089,13 @@ cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_
 		a.kout = to_out ? keys_out : s.tmp_keys;
 		a.vout = to_out ? vals_out : s.tmp_vals;
 		a.n = (uint32_t)n;
+		a.out_cap = (uint32_t)n;
 		a.shift = h.shift[p];
 		a.bits = h.bits[p];
 		a.hist = s.hist + p * RADIX;
 		a.status = s.status + (size_t)p * tiles * RADIX;
 		a.ticket = s.ctl + p;
-		onesweep_kernel<<<tiles, OS_THREADS, 0, stream>>>(a);
-		count_launch();
+		launch_onesweep(a, n, stream);
 		kin = a.kout;
 		vin = a.vout;
 	}

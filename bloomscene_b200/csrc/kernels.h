@@ -86,7 +86,7 @@ enum HeaderWord : int {
 	HDR_KEY_INVMIN = 2, // max over visible Gaussians of ~depth bits (= ~min)
 	HDR_KEY_MAX = 3,    // max depth bits over visible Gaussians
 	HDR_V = 4,          // visible Gaussians
-	HDR_OVERFLOW = 5,   // bit 0: R > R_cap, bit 1: R1 > R1_cap, bit 2: depth keys need more bits than planned
+	HDR_OVERFLOW = 5,   // bit 0: R > R_cap, bit 1: R1 > R1_cap, bit 2: depth keys need more bits than planned, bit 3: V > V_cap
 	HDR_KEY_BITS = 6,   // significant bits of (max key - bias)
 	HDR_WORDS = 8
 };
@@ -98,14 +98,15 @@ enum InstCtl : int { ICTL_EMIT_TICKET = 0, ICTL_EMIT_DONE = 1, ICTL_N_INSTANCES 
 struct DepthScratch {
 	uint32_t* ctl;    // [DCTL_WORDS]
 	uint32_t* hist;   // [4][256]
-	uint32_t* status; // [passes][tiles][256]
+	uint32_t* status; // [tiles][256] of the first pass, then [passes - 1][tiles_rest][256]
 	uint32_t* keys[2];
 	uint32_t* vals[2];
-	uint32_t tiles;
+	uint32_t tiles;      // tiles of the first pass (over P keys)
+	uint32_t tiles_rest; // tiles of the later passes (over at most V_cap keys)
 };
-size_t depth_zero_bytes(size_t P, int passes);
+size_t depth_zero_bytes(size_t P, size_t V_cap, int passes);
 size_t depth_plain_bytes(size_t P);
-DepthScratch carve_depth_scratch(void* zeroed, void* plain, size_t P, int passes);
+DepthScratch carve_depth_scratch(void* zeroed, void* plain, size_t P, size_t V_cap, int passes);
 
 // Scratch of the instance levels (emission, coarse sort, fine binning), sized by the CAPACITY R1_cap.
 struct InstScratch {
@@ -133,6 +134,7 @@ InstScratch carve_inst_scratch(void* zeroed, void* plain, size_t P, size_t R1_ca
 // One forward's binning: capacities from the host, counts from the header on the device.
 struct BinPlan {
 	uint32_t P, R1_cap, R_cap;
+	uint32_t V_cap;            // capacity of the visible Gaussians: sizes the depth sort's passes after the first
 	uint32_t grid_x, grid_y, ns_x, ns;
 	int depth_passes;          // 8-bit digits of (depth key - bias) that are sorted on
 	uint32_t* hdr;             // geometry header

@@ -151,7 +151,8 @@ int brs_forward(const brs_view* view, const brs_gaussians* g,
  *                    overflow word) the binning and the blend are run again with the exact sizes.
  *   BRS_FWD_EXACT    wait for the counts right after preprocess, then size exactly (reference behaviour).
  *   BRS_FWD_DEFERRED no host wait at all: capacities from this struct (0 = the high-water marks); the
- *                    8-word header {R, R1, ~min depth key, max depth key, V, overflow, key bits, 0} is copied
+ *                    8-word header {R, R1, ~min depth key, max depth key, V, overflow, key bits, 0} (overflow: bit 0
+ *                    R, bit 1 R1, bit 2 depth-key bits, bit 3 V exceeded its capacity) is copied
  *                    asynchronously to `report` (pinned host memory).  state->num_rendered is -1.  The caller
  *                    inspects report[5] after it has synchronised with the stream for its own reasons — e.g.
  *                    once per batch of views — and repeats the overflowed forwards in EXACT mode.  A deferred

@@ -614,6 +614,28 @@ def test_forward_modes_are_bit_identical_and_an_overflow_reruns():
     far_exact = _fwd_ex(_C, far, cam, bg, _C.FWD_EXACT)
     _same_forward(_C, far_exact, far_auto, P, W, H)
 
+    # the visible count is a capacity too (it sizes the depth sort's later passes): marks from a view that sees few
+    # Gaussians, then a view that sees many more with FEWER instances each -> only the V capacity overflows -> re-run
+    _C.reset_marks()
+    away = synthetic.Scene(scene.means3D.clone(), scene.scales, scene.rotations, scene.opacities, scene.shs, None, scene.sh_degree)
+    away.means3D[: P - 300, 2] -= 50.0     # all but 300 Gaussians behind the camera
+    few = _fwd_ex(_C, away, cam, bg, _C.FWD_EXACT, mod=6.0)
+    assert 0 < int((few[3] > 0).sum()) <= 300
+    before = _C.forward_stats(False)["overflow_reruns"]
+    many_auto = _fwd_ex(_C, scene, cam, bg, _C.FWD_AUTO, mod=0.05)
+    assert _C.forward_stats(False)["overflow_reruns"] == before + 1
+    many_exact = _fwd_ex(_C, scene, cam, bg, _C.FWD_EXACT, mod=0.05)
+    assert int((many_exact[3] > 0).sum()) > 5000
+    _same_forward(_C, many_exact, many_auto, P, W, H)
+    rep = torch.zeros(8, dtype=torch.int32).pin_memory()
+    _C.reset_marks()
+    _fwd_ex(_C, away, cam, bg, _C.FWD_EXACT, mod=6.0)
+    _fwd_ex(_C, scene, cam, bg, _C.FWD_DEFERRED, mod=0.05, R_cap=1 << 22, R1_cap=1 << 22, report=rep)
+    torch.cuda.synchronize()
+    assert int(rep[5]) & 8, rep        # bit 3 of the overflow word: V > V_cap
+    _C.reset_marks()
+    _fwd_ex(_C, scene, cam, bg, _C.FWD_EXACT)
+
     # DEFERRED: no host wait; counts arrive in the pinned report
     report = torch.zeros(8, dtype=torch.int32).pin_memory()
     dfr = _fwd_ex(_C, scene, cam, bg, _C.FWD_DEFERRED, report=report)

@@ -40,7 +40,7 @@ static float median(std::vector<float> v)
 int main(int argc, char** argv)
 {
 	const int iters = argc > 1 ? atoi(argv[1]) : 50;
-	const int sizes[] = {100000, 1000000, 3000000};
+	const int sizes[] = {50000, 100000, 250000, 500000, 1000000, 3000000};
 	const char* dists[] = {"uniform24", "depth"};
 	cudaStream_t stream;
 	CK(cudaStreamCreate(&stream));

@@ -302,7 +302,10 @@ def test_sort_pairs_is_a_stable_radix_sort():
     from bloomscene_b200 import _C
 
     g = torch.Generator(device="cpu").manual_seed(5)
-    for n, hi in [(0, 32), (1, 32), (33, 32), (4096, 9), (4097, 32), (123_457, 13), (1_000_003, 32), (3_000_000, 15)]:
+    # sizes on both sides of every tile size (1024 / 2048 / 4096 pairs) and of the capacity thresholds that pick it
+    # (128 K and 384 K pairs: 4, 8 or 16 keys per thread, binning.cu sort_items)
+    for n, hi in [(0, 32), (1, 32), (33, 32), (1024, 32), (1025, 7), (4096, 9), (4097, 32), (123_457, 13), (131_072, 32),
+                  (131_073, 24), (250_001, 32), (393_216, 17), (393_217, 32), (1_000_003, 32), (3_000_000, 15)]:
         keys = torch.randint(0, 2 ** 31 - 1, (n,), generator=g, dtype=torch.int64)
         if hi < 32:
             keys &= (1 << hi) - 1

@@ -115,7 +115,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 				const f32x2 nt3 = mul2(ndy, bc2(dxb));
 				const f32x2 power = fma2(s, bc2(-0.5f), nt3);
 				// a saturated pixel multiplies its alpha by live = 0 (exact: o*G*1 == o*G), so the loop
-				// carries no per-pixel `done` test
+				// carries no per-pixel `done` test.  A non-finite opacity turns that product into NaN and
+				// fminf(0.99, NaN) = 0.99, but a finished pixel cannot be revived by it: it stopped with
+				// T * (1 - alpha) < 1e-4 for some alpha <= 0.99, i.e. T < 1e-2, so T * (1 - 0.99) < 1e-4 and the
+				// saturation branch below discards the record again (measured: masking by predicate instead
+				// costs 1 % of the kernel; tests/test_gpu_parity.py::test_non_finite_inputs_... covers the case)
 				const f32x2 oG = mul2(mul2(bc2(con.w), expf_exact2(power, ek)), pk2(live));
 				const float alpha0 = fminf(0.99f, lo2(oG)), alpha1 = fminf(0.99f, hi2(oG));
 				const bool ok0 = !(lo2(power) > 0.0f) && !(alpha0 < 1.0f / 255.0f);

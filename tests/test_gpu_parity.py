@@ -224,6 +224,24 @@ def test_non_finite_inputs_vs_reference_cuda():
     okd = torch.isfinite(dr)
     assert torch.equal(torch.isfinite(do), okd) and (do[okd] - dr[okd]).abs().max().item() <= pl.COLOR_TOL
 
+    # a NaN / inf opacity BEHIND pixels that have already saturated: the reference never touches a finished pixel
+    # (`done`), fminf(0.99, NaN) = 0.99 must not revive it
+    s = synthetic.make_scene(900, "object", "precomp", -3.0, seed=14)
+    s.means3D[0] = torch.tensor([0.0, 0.0, -1.5])          # a huge opaque Gaussian in front of everything
+    s.scales[0] = torch.tensor([0.8, 0.8, 0.8])
+    s.opacities[:60] = 1.0
+    s.opacities[400] = float("nan")
+    s.opacities[401] = float("inf")
+    s.opacities[402] = float("-inf")
+    s = s.to(DEV)
+    rep = pl.compare_stages(s, cam, bg)
+    assert rep["point_list_mismatch"] == 0 and rep["n_contrib_mismatch"] == 0 and rep["final_T_mismatch"] == 0, rep
+    _, co, do, _ = render(mine, s)
+    _, cr, dr, _ = render(ref, s)
+    ok = torch.isfinite(cr)
+    assert torch.equal(torch.isfinite(co), ok) and (co[ok] - cr[ok]).abs().max().item() <= pl.COLOR_TOL
+    assert (cr[ok] < 1e30).all()
+
     # NaN scale -> NaN covariance -> radius (int)NaN = 0 with a one-tile rect.  The reference counts that instance but
     # never writes its key (`if (radii[idx] > 0)`, rasterizer_impl.cu:85) and sorts an uninitialised slot; here the
     # Gaussian is culled: same image as with the Gaussian behind the camera.

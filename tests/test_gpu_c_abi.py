@@ -55,6 +55,8 @@ def _lib():
     lib.brs_visible_filter.argtypes = [C.POINTER(View), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
     lib.brs_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.brs_forward_views.argtypes = [C.POINTER(View), C.c_int, C.POINTER(Gaussians), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      ALLOC, C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p, C.c_void_p]
     lib.brs_error_string.restype = C.c_char_p
     return lib
 
@@ -170,3 +172,48 @@ def test_filter_and_mark_visible_through_ctypes_only():
                                 present.data_ptr(), stream) == 0
     torch.cuda.synchronize()
     assert torch.equal(present.bool(), api.GaussianRasterizer(rs).markVisible(scene.means3D))
+
+
+def test_forward_views_through_ctypes_only():
+    """brs_forward_views: a stack of views with DIFFERENT fields of view and scale modifiers as one pipeline, driven
+    with plain structs; every view equals a brs_forward of its own, and num_rendered is the sum."""
+    lib = _lib()
+    W, H = 150, 94
+    scene = synthetic.make_scene(6000, "object", "sh2", -3.4, seed=33).to(DEV)
+    bg = torch.tensor([0.2, 0.4, 0.1], device=DEV)
+    M, P = scene.shs.shape[1], scene.P
+    cams = [synthetic.orbit_camera(W, H, 0.5 * k).to(DEV) for k in range(5)]
+    mods = [1.0, 0.7, 1.0, 1.6, 0.4]
+    fovs = [1.0, 1.2, 0.8, 1.0, 1.5]  # tan-fov factors: the projection matrix stays, the focal length changes
+    views = (View * len(cams))(*[
+        View(W, H, c.tanfovx * f, c.tanfovy * f, m, scene.sh_degree, M, 0, 0, _ptr(bg), _ptr(c.viewmatrix), _ptr(c.projmatrix),
+             _ptr(c.campos)) for c, m, f in zip(cams, mods, fovs)])
+    g = Gaussians(P, _ptr(scene.means3D), _ptr(scene.opacities), _ptr(scene.shs), None, _ptr(scene.scales),
+                  _ptr(scene.rotations), None)
+    n = len(cams)
+    color = torch.empty(n, 3, H, W, device=DEV)
+    depth = torch.empty(n, 1, H, W, device=DEV)
+    radii = torch.empty(n, P, dtype=torch.int32, device=DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    arena, total = Arena(), C.c_longlong(-7)
+    rc = lib.brs_forward_views(views, n, C.byref(g), color.data_ptr(), depth.data_ptr(), radii.data_ptr(), arena.fn, None,
+                               C.byref(total), None, stream)
+    assert rc == 0, lib.brs_error_string(rc)
+    torch.cuda.synchronize()
+    R_sum = 0
+    for k in range(n):
+        c1 = torch.empty(3, H, W, device=DEV)
+        d1 = torch.empty(1, H, W, device=DEV)
+        r1 = torch.empty(P, dtype=torch.int32, device=DEV)
+        a1, st = Arena(), FwdState()
+        one = View(*[getattr(views[k], f) for f, _ in View._fields_])
+        assert lib.brs_forward(C.byref(one), C.byref(g), c1.data_ptr(), d1.data_ptr(), r1.data_ptr(), a1.fn, None, C.byref(st),
+                               stream) == 0
+        torch.cuda.synchronize()
+        R_sum += st.num_rendered
+        assert torch.equal(r1, radii[k]) and torch.equal(c1, color[k]) and torch.equal(d1, depth[k]), k
+    assert total.value == R_sum > 0
+    # one view of the stack with another image size: rejected
+    views[2].image_width = W + 16
+    assert lib.brs_forward_views(views, n, C.byref(g), color.data_ptr(), depth.data_ptr(), radii.data_ptr(), arena.fn, None,
+                                 C.byref(total), None, stream) == -1

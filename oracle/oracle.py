@@ -74,6 +74,7 @@ def lib():
         L.orc_backward.restype = C.c_int
         L.orc_backward_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Grads)]
         L.orc_backward_ex.restype = C.c_int
+        L.orc_set_f64_sums.argtypes = [C.c_int]
         L.orc_visible_filter.argtypes = [C.POINTER(_Inputs), C.c_int, C.c_void_p]
         L.orc_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
@@ -150,7 +151,7 @@ class Oracle:
         R = self.L.orc_forward(self.ctx, C.byref(inp), _ptr(color), _ptr(depth), _ptr(radii))
         return R, color, depth, radii
 
-    def backward(self, dL_dcolor, dL_ddepth=None) -> Dict[str, np.ndarray]:
+    def backward(self, dL_dcolor, dL_ddepth=None, f64_sums: bool = False) -> Dict[str, np.ndarray]:
         """Gradients in the reference's shapes (rasterize_points.cu:154-162). Call after forward().
         `dL_ddepth` (default None = the reference: depth carries no gradient) switches on the opt-in
         depth-gradient extension."""
@@ -162,8 +163,14 @@ class Oracle:
              "dL_dcov3D": np.zeros((P, 6), np.float32), "dL_dsh": np.zeros((P, M, 3), np.float32),
              "dL_dscales": np.zeros((P, 3), np.float32), "dL_drotations": np.zeros((P, 4), np.float32)}
         gs = _Grads(*[_ptr(g[n]) if g[n].size else None for n, _ in _Grads._fields_])
-        if P:
-            self.L.orc_backward_ex(self.ctx, _ptr(d), _ptr(dd), C.byref(gs))
+        # f64_sums (diagnostic): the per-Gaussian sums of the blend backward are accumulated in double and rounded
+        # once, which separates summation error from arithmetic differences
+        self.L.orc_set_f64_sums(1 if f64_sums else 0)
+        try:
+            if P:
+                self.L.orc_backward_ex(self.ctx, _ptr(d), _ptr(dd), C.byref(gs))
+        finally:
+            self.L.orc_set_f64_sums(0)
         return g
 
     def visible_filter(self, scales_stride: int = 3, **kw) -> np.ndarray:

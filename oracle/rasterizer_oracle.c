@@ -596,10 +596,24 @@ int orc_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8
 
 /* ---- backward ---------------------------------------------------------------------------------- */
 
-static void atomic_addf(float* p, float v)
+/* Diagnostic (tests only): with orc_set_f64_sums(1) the per-Gaussian sums of the blend backward — the same fp32
+ * per-pixel terms — are accumulated in DOUBLE and rounded to float once, before the per-Gaussian stage consumes them.
+ * This separates summation error (the reference adds up to W*H float terms into one float with atomicAdd,
+ * backward.cu:556-575) from arithmetic differences when two implementations disagree on a gradient.  Default off. */
+static int g_f64_sums = 0;
+void orc_set_f64_sums(int enable) { g_f64_sums = enable != 0; }
+typedef struct sum64 { /* shadows of the float accumulators, NULL when the diagnostic is off */
+	double *mean2D, *conic, *opacity, *colors, *z;
+} sum64;
+static void acc_add(float* f, double* d, size_t i, float v)
 {
+	if (d) {
 #pragma omp atomic
-	*p += v;
+		d[i] += (double)v;
+	} else {
+#pragma omp atomic
+		f[i] += v;
+	}
 }
 
 /* renderCUDA backward for one pixel (backward.cu:399-586). dL_dconic is [P][4] (x, y, -, w). */
@@ -611,7 +625,7 @@ static void atomic_addf(float* p, float v)
  * channel (accum_depth_rec / last_depth), and z collects dL_dz = sum alpha T gD. */
 static void render_pixel_backward(const orc_ctx* c, int px, int py, uint32_t start, uint32_t end, const float* colors,
                                   const float* dL_dpixels, const float* dL_ddepths, float* dL_dmean2D, float* dL_dconic,
-                                  float* dL_dopacity, float* dL_dcolors, float* dL_dz)
+                                  float* dL_dopacity, float* dL_dcolors, float* dL_dz, const sum64* s64)
 {
 	const int W = c->W, H = c->H;
 	const uint32_t pix_id = (uint32_t)W * py + px;
@@ -654,7 +668,7 @@ static void render_pixel_backward(const orc_ctx* c, int px, int py, uint32_t sta
 			last_color[ch] = col;
 			const float dL_dchannel = dL_dpixel[ch];
 			dL_dalpha += (col - accum_rec[ch]) * dL_dchannel;
-			atomic_addf(&dL_dcolors[id * NCH + ch], dchannel_dcolor * dL_dchannel);
+			acc_add(dL_dcolors, s64->colors, (size_t)id * NCH + ch, dchannel_dcolor * dL_dchannel);
 		}
 		if (dL_ddepths) {
 			const float c_d = c->depths[id];
@@ -664,7 +678,7 @@ static void render_pixel_backward(const orc_ctx* c, int px, int py, uint32_t sta
 			accum_one_rec = last_alpha * last_one + (1.f - last_alpha) * accum_one_rec;
 			last_one = 1.f;
 			dL_dalpha += (1.f - accum_one_rec) * gA;
-			atomic_addf(&dL_dz[id], dchannel_dcolor * gD);
+			acc_add(dL_dz, s64->z, id, dchannel_dcolor * gD);
 		}
 		dL_dalpha *= T;
 		last_alpha = alpha;
@@ -676,12 +690,12 @@ static void render_pixel_backward(const orc_ctx* c, int px, int py, uint32_t sta
 		const float gdx = G * dx, gdy = G * dy;
 		const float dG_ddelx = -gdx * con_o[0] - gdy * con_o[1];
 		const float dG_ddely = -gdy * con_o[2] - gdx * con_o[1];
-		atomic_addf(&dL_dmean2D[3 * id], dL_dG * dG_ddelx * ddelx_dx);
-		atomic_addf(&dL_dmean2D[3 * id + 1], dL_dG * dG_ddely * ddely_dy);
-		atomic_addf(&dL_dconic[4 * id], -0.5f * gdx * dx * dL_dG);
-		atomic_addf(&dL_dconic[4 * id + 1], -0.5f * gdx * dy * dL_dG);
-		atomic_addf(&dL_dconic[4 * id + 3], -0.5f * gdy * dy * dL_dG);
-		atomic_addf(&dL_dopacity[id], G * dL_dalpha);
+		acc_add(dL_dmean2D, s64->mean2D, 3 * (size_t)id, dL_dG * dG_ddelx * ddelx_dx);
+		acc_add(dL_dmean2D, s64->mean2D, 3 * (size_t)id + 1, dL_dG * dG_ddely * ddely_dy);
+		acc_add(dL_dconic, s64->conic, 4 * (size_t)id, -0.5f * gdx * dx * dL_dG);
+		acc_add(dL_dconic, s64->conic, 4 * (size_t)id + 1, -0.5f * gdx * dy * dL_dG);
+		acc_add(dL_dconic, s64->conic, 4 * (size_t)id + 3, -0.5f * gdy * dy * dL_dG);
+		acc_add(dL_dopacity, s64->opacity, id, G * dL_dalpha);
 	}
 }
 
@@ -882,6 +896,14 @@ int orc_backward_ex(orc_ctx* c, const float* dL_dpixels, const float* dL_ddepths
 	float* dL_dz = (float*)calloc((size_t)P, sizeof(float));
 	const float* colors = c->colors_precomp ? c->colors_precomp : c->rgb; /* rasterizer_impl.cu:453 */
 	const int ntiles = c->gx * c->gy;
+	sum64 s64 = {NULL, NULL, NULL, NULL, NULL};
+	if (g_f64_sums) {
+		s64.mean2D = (double*)calloc((size_t)3 * P, sizeof(double));
+		s64.conic = (double*)calloc((size_t)4 * P, sizeof(double));
+		s64.opacity = (double*)calloc((size_t)P, sizeof(double));
+		s64.colors = (double*)calloc((size_t)3 * P, sizeof(double));
+		s64.z = (double*)calloc((size_t)P, sizeof(double));
+	}
 #pragma omp parallel for schedule(dynamic, 1)
 	for (int tile = 0; tile < ntiles; tile++) {
 		const int tx = tile % c->gx, ty = tile / c->gx;
@@ -892,8 +914,16 @@ int orc_backward_ex(orc_ctx* c, const float* dL_dpixels, const float* dL_ddepths
 				const int px = tx * BLOCK_X + lx, py = ty * BLOCK_Y + ly;
 				if (px < W && py < H)
 					render_pixel_backward(c, px, py, start, end, colors, dL_dpixels, dL_ddepths, g->dL_dmeans2D, dL_dconic,
-					                      g->dL_dopacity, g->dL_dcolors, dL_dz);
+					                      g->dL_dopacity, g->dL_dcolors, dL_dz, &s64);
 			}
+	}
+	if (g_f64_sums) { /* round the double sums once */
+		for (size_t i = 0; i < (size_t)3 * P; i++) g->dL_dmeans2D[i] = (float)s64.mean2D[i];
+		for (size_t i = 0; i < (size_t)4 * P; i++) dL_dconic[i] = (float)s64.conic[i];
+		for (size_t i = 0; i < (size_t)P; i++) g->dL_dopacity[i] = (float)s64.opacity[i];
+		for (size_t i = 0; i < (size_t)3 * P; i++) g->dL_dcolors[i] = (float)s64.colors[i];
+		for (size_t i = 0; i < (size_t)P; i++) dL_dz[i] = (float)s64.z[i];
+		free(s64.mean2D); free(s64.conic); free(s64.opacity); free(s64.colors); free(s64.z);
 	}
 	const float* cov3D_all = c->cov3D_precomp ? c->cov3D_precomp : c->cov3D; /* rasterizer_impl.cu:481 */
 #pragma omp parallel for schedule(static)

@@ -272,3 +272,24 @@ def test_opt_in_depth_gradient_with_oracle_backend():
             index = tuple(int(v) for v in np.unravel_index(i, t.shape))
             errs.append(abs(fd(t, index, eps) - t.grad[index].item()) / abs(t.grad[index].item()))
         assert sorted(errs)[2] <= 0.02, errs
+
+
+def test_oracle_double_precision_sums_agree_with_float_sums_on_a_small_scene():
+    """Oracle.backward(f64_sums=True) — the referee of the screen-filling-Gaussians gradient test — changes only the
+    ACCUMULATION of the per-Gaussian sums: on a small scene (short sums) it agrees with the fp32 sums to float rounding,
+    and it leaves no state behind."""
+    from oracle import oracle
+    from workload import synthetic
+
+    scene = synthetic.make_scene(300, "object", "sh1", -2.8, seed=4)
+    cam = synthetic.orbit_camera(48, 40, 0.3)
+    Wc, _ = synthetic.loss_weights(48, 40, seed=2)
+    o = oracle.run_scene(scene, cam, torch.tensor([0.1, 0.2, 0.3]))["oracle"]
+    a = o.backward(Wc.numpy())
+    b = o.backward(Wc.numpy(), f64_sums=True)
+    c = o.backward(Wc.numpy())
+    for k in a:
+        na = np.linalg.norm(a[k])
+        assert np.linalg.norm(a[k] - b[k]) <= 2e-6 * max(na, 1e-30), k
+        assert np.linalg.norm(a[k] - c[k]) <= 2e-6 * max(na, 1e-30), k   # fp32 again (OpenMP order noise only)
+    assert np.abs(a["dL_dopacity"]).sum() > 0

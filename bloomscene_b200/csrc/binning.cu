@@ -157,15 +157,26 @@ __global__ void __launch_bounds__(OS_THREADS) radix_hist_kernel(HistArgs a)
 		if (a.overflow_accum != nullptr && flags != 0u)
 			atomicOr(a.overflow_accum, flags);
 	}
-	for (uint32_t i = blockIdx.x * OS_THREADS + tid; i < n; i += gridDim.x * OS_THREADS) {
-		const uint32_t key = __ldg(a.keys + i);
-		if (a.drop && key == DEPTH_KEY_CULLED)
-			continue;
-		const uint32_t k = key - bias;
+	// four independent loads in flight per thread (a plain grid-stride loop exposes one load latency per key)
+	const uint32_t stride = gridDim.x * OS_THREADS;
+	for (uint32_t i0 = blockIdx.x * OS_THREADS + tid; i0 < n; i0 += 4 * stride) {
+		uint32_t key[4];
 #pragma unroll
-		for (int p = 0; p < 4; p++)
-			if (p < a.passes)
-				atomicAdd(&s_hist[p][(k >> a.shift[p]) & ((1u << a.bits[p]) - 1u)], 1u);
+		for (int j = 0; j < 4; j++) {
+			const uint32_t i = i0 + j * stride;
+			key[j] = (i >= i0 && i < n) ? __ldg(a.keys + i) : DEPTH_KEY_CULLED; // i >= i0: no 32-bit wrap-around
+		}
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const uint32_t i = i0 + j * stride;
+			if (!(i >= i0 && i < n) || (a.drop && key[j] == DEPTH_KEY_CULLED))
+				continue;
+			const uint32_t k = key[j] - bias;
+#pragma unroll
+			for (int p = 0; p < 4; p++)
+				if (p < a.passes)
+					atomicAdd(&s_hist[p][(k >> a.shift[p]) & ((1u << a.bits[p]) - 1u)], 1u);
+		}
 	}
 	__syncthreads();
 	for (int i = tid; i < a.passes * RADIX; i += OS_THREADS) {
@@ -173,6 +184,11 @@ __global__ void __launch_bounds__(OS_THREADS) radix_hist_kernel(HistArgs a)
 		if (c)
 			atomicAdd(a.hist + i, c);
 	}
+}
+
+inline uint32_t hist_blocks(size_t n) // 2048 keys per CTA, at most 4 CTAs per SM (measured: 296 ... 1184 CTAs within 3 %)
+{
+	return (uint32_t)std::max<size_t>(1, std::min<size_t>((n + 2047) / 2048, 592));
 }
 
 // ---- one radix pass ---------------------------------------------------------------------------------
@@ -914,7 +930,7 @@ cudaError_t launch_depth_sort_begin(const BinPlan& pl, int planned_passes, cudaS
 	h.V_cap = pl.V_cap;
 	h.overflow_accum = pl.overflow_accum;
 	h.hist = pl.d.hist;
-	const uint32_t hist_grid = (uint32_t)std::min<size_t>((pl.P + 2047) / 2048, 296);
+	const uint32_t hist_grid = hist_blocks(pl.P);
 	radix_hist_kernel<<<hist_grid, OS_THREADS, 0, stream>>>(h);
 	count_launch();
 	launch_onesweep(depth_pass_args(pl, 0), pl.P, stream);
@@ -1077,7 +1093,7 @@ cudaError_t sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_
 	}
 	h.hist = s.hist;
 	const uint32_t tiles = sort_tiles(n);
-	radix_hist_kernel<<<(uint32_t)std::min<size_t>((n + 2047) / 2048, 296), OS_THREADS, 0, stream>>>(h);
+	radix_hist_kernel<<<hist_blocks(n), OS_THREADS, 0, stream>>>(h);
 	count_launch();
 	const uint32_t* kin = keys_in;
 	const uint32_t* vin = vals_in;

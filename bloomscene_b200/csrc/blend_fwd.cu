@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 				// a pixel that skips the record blends alpha = 0: T * (1 - 0) == T and fma(T, 0 * col, C) == C
 				F2 al = {ok0 ? alpha0 : 0.f, ok1 ? alpha1 : 0.f};
 				const f32x2 Tp = pk2(T);
-				F2 test_T = unpk2(mul2(Tp, sub2(bc2(1.0f), pk2(al))));
+				const F2 test_T = unpk2(mul2(Tp, sub2(bc2(1.0f), pk2(al))));
 				const uint32_t pos = (uint32_t)(base + c0 + j + 1);
-				uint32_t nl0 = ok0 ? pos : last0, nl1 = ok1 ? pos : last1;
+				bool take0 = ok0, take1 = ok1, keep0 = false, keep1 = false;
 				if (fminf(test_T.lo, test_T.hi) < 0.0001f) {
 					// rare (once per pixel): the record that would saturate the pixel is not blended
 					// (reference forward.cu:431-436) and the pixel stops
@@ -140,20 +140,22 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 					live.hi = s1 ? 0.f : live.hi;
 					al.lo = s0 ? 0.f : al.lo;
 					al.hi = s1 ? 0.f : al.hi;
-					test_T.lo = s0 ? T.lo : test_T.lo;
-					test_T.hi = s1 ? T.hi : test_T.hi;
-					nl0 = s0 ? last0 : nl0;
-					nl1 = s1 ? last1 : nl1;
+					take0 = take0 && !s0;
+					take1 = take1 && !s1;
+					keep0 = s0;
+					keep1 = s1;
 				}
-				last0 = nl0;
-				last1 = nl1;
+				// state is updated in place after the rare branch (no old / new pair live across it)
+				last0 = take0 ? pos : last0;
+				last1 = take1 ? pos : last1;
+				T.lo = keep0 ? T.lo : test_T.lo;
+				T.hi = keep1 ? T.hi : test_T.hi;
 				const f32x2 alp = pk2(al);
 				C0 = unpk2(fma2(mul2(alp, bc2(col.x)), Tp, pk2(C0)));
 				C1 = unpk2(fma2(mul2(alp, bc2(col.y)), Tp, pk2(C1)));
 				C2 = unpk2(fma2(mul2(alp, bc2(col.z)), Tp, pk2(C2)));
 				D = unpk2(fma2(mul2(alp, bc2(col.w)), Tp, pk2(D)));
 				acc = unpk2(fma2(alp, Tp, pk2(acc)));
-				T = test_T;
 			} while (mask);
 		}
 	}

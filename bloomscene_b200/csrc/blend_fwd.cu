@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 	const uint32_t* list = a.point_list + range.x;
 
 	bool done0 = !inside0, done1 = !inside1;
-	F2 T = {1.0f, 1.0f};
+	F2 T = {1.0f, 1.0f}, T2 = {1.0f, 1.0f};
 	F2 live = {done0 ? 0.f : 1.f, done1 ? 0.f : 1.f};
 	uint32_t last0 = 0, last1 = 0;
 	F2 C0 = {0.f, 0.f}, C1 = C0, C2 = C0, D = C0, acc = {0.000001f, 0.000001f};
@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 			if (e < cnt)
 				hit = block_may_contribute(rec[e].geo, rec[e].con, wx0, wx1, wy0, wy1);
 			uint32_t mask = __ballot_sync(0xffffffffu, hit);
-			if (mask) do {
+			// one record for the warp's 64 pixels; the transmittance goes Tin -> Tout so that two calls per loop trip
+			// ping-pong between two register pairs (a single pair costs a register-move pair per record)
+			auto blend_one = [&](const F2& Tin, F2& Tout) {
 				const int j = __ffs(mask) - 1;
 				mask &= mask - 1;
 				const StagedRecord* r = rec + (c0 + j);
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 				const bool ok1 = !(hi2(power) > 0.0f) && !(alpha1 < 1.0f / 255.0f);
 				// a pixel that skips the record blends alpha = 0: T * (1 - 0) == T and fma(T, 0 * col, C) == C
 				F2 al = {ok0 ? alpha0 : 0.f, ok1 ? alpha1 : 0.f};
-				const f32x2 Tp = pk2(T);
+				const f32x2 Tp = pk2(Tin);
 				const F2 test_T = unpk2(mul2(Tp, sub2(bc2(1.0f), pk2(al))));
 				const uint32_t pos = (uint32_t)(base + c0 + j + 1);
 				bool take0 = ok0, take1 = ok1, keep0 = false, keep1 = false;
@@ -148,14 +150,22 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 				// state is updated in place after the rare branch (no old / new pair live across it)
 				last0 = take0 ? pos : last0;
 				last1 = take1 ? pos : last1;
-				T.lo = keep0 ? T.lo : test_T.lo;
-				T.hi = keep1 ? T.hi : test_T.hi;
+				Tout.lo = keep0 ? Tin.lo : test_T.lo;
+				Tout.hi = keep1 ? Tin.hi : test_T.hi;
 				const f32x2 alp = pk2(al);
 				C0 = unpk2(fma2(mul2(alp, bc2(col.x)), Tp, pk2(C0)));
 				C1 = unpk2(fma2(mul2(alp, bc2(col.y)), Tp, pk2(C1)));
 				C2 = unpk2(fma2(mul2(alp, bc2(col.z)), Tp, pk2(C2)));
 				D = unpk2(fma2(mul2(alp, bc2(col.w)), Tp, pk2(D)));
 				acc = unpk2(fma2(alp, Tp, pk2(acc)));
+			};
+			if (mask) do {
+				blend_one(T, T2);
+				if (!mask) {
+					T = T2;
+					break;
+				}
+				blend_one(T2, T);
 			} while (mask);
 		}
 	}

@@ -324,6 +324,10 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				mask &= mask - 1;
 				const int idx = c0 + j;
 				const StagedRecord* r = rec + idx;
+				// the behind-colour recurrence only needs loop-carried values: formed first, so that the previous
+				// record's alpha is dead by the time this record's alpha is selected (it then lands in the same registers)
+				const f32x2 b_old = pk2(beta);
+				const f32x2 bn = fma2(pk2(last_alpha), sub2(pk2(last_cd), b_old), b_old);
 				const float2 g = *reinterpret_cast<const float2*>(&r->geo);
 				const float4 con = r->con;
 				const float dx = g.x - pixfx;
@@ -356,8 +360,6 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				// (accum_rec) and sums (c - accum_rec) * dL_dpixel over the channels.  Only that sum is
 				// needed, so the recurrence runs on its projection: beta = accum_rec . dL_dpixel and
 				// cd = colour . dL_dpixel are scalars.
-				const f32x2 b_old = pk2(beta);
-				const f32x2 bn = fma2(pk2(last_alpha), sub2(pk2(last_cd), b_old), b_old);
 				f32x2 cd = fma2(bc2(col.z), dpx2, fma2(bc2(col.y), dpx1, mul2(bc2(col.x), dpx0)));
 				if (DEPTH)
 					cd = add2(fma2(bc2(col.w), gD2, cd), gA2);

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				*reinterpret_cast<float2*>(st) = w2;
 				*reinterpret_cast<float2*>(st + STAGE_U) = u2;
 				if (lane == 0)
-					stage[staged * STAGE_STRIDE + STAGE_SLOT] = __int_as_float(idx); // the record's batch slot
+					st[STAGE_SLOT] = __int_as_float(idx); // the record's batch slot (lane 0's stage_off is 0: st == slot base)
 				st += STAGE_STRIDE;
 				if (++staged == GROUP) {
 					flush_group<DEPTH>(stage, GROUP, rec, s_id, dpx_rows, wx0, wy0, lane, a.accum);

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(BlendFwdAr
 				const F2 test_T = unpk2(mul2(Tp, sub2(bc2(1.0f), pk2(al))));
 				const uint32_t pos = (uint32_t)(base + c0 + j + 1);
 				bool take0 = ok0, take1 = ok1, keep0 = false, keep1 = false;
-				if (fminf(test_T.lo, test_T.hi) < 0.0001f) {
+				if (__any_sync(0xffffffffu, fminf(test_T.lo, test_T.hi) < 0.0001f)) { // warp-uniform: no reconvergence point
 					// rare (once per pixel): the record that would saturate the pixel is not blended
 					// (reference forward.cu:431-436) and the pixel stops
 					const bool s0 = test_T.lo < 0.0001f, s1 = test_T.hi < 0.0001f;

@@ -324,10 +324,6 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 				mask &= mask - 1;
 				const int idx = c0 + j;
 				const StagedRecord* r = rec + idx;
-				// the behind-colour recurrence only needs loop-carried values: formed first, so that the previous
-				// record's alpha is dead by the time this record's alpha is selected (it then lands in the same registers)
-				const f32x2 b_old = pk2(beta);
-				const f32x2 bn = fma2(pk2(last_alpha), sub2(pk2(last_cd), b_old), b_old);
 				const float2 g = *reinterpret_cast<const float2*>(&r->geo);
 				const float4 con = r->con;
 				const float dx = g.x - pixfx;
@@ -347,6 +343,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(BlendBwdA
 					continue;
 
 				const float4 col = r->col;
+				// the behind-colour recurrence only needs loop-carried values: formed right after the skip test and
+				// before this record's alpha is selected, so that it updates beta in place and the previous record's
+				// alpha is dead by the time the new one lands in its registers
+				const f32x2 b_old = pk2(beta);
+				const f32x2 bn = fma2(pk2(last_alpha), sub2(pk2(last_cd), b_old), b_old);
 				// a pixel that skips the record runs the chain with alpha = 0 (see the header)
 				const f32x2 al = pk2(ok0 ? alpha0 : 0.f, ok1 ? alpha1 : 0.f);
 				// 1 - alpha >= 0.01 (alpha is clamped to 0.99): one MUFU.RCP (<= 1 ulp, exact for 1.0) replaces the

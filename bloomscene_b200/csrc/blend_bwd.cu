@@ -88,11 +88,19 @@ __device__ __forceinline__ void flush_group(const float* __restrict__ stage, int
 		// phase 1: the moments of w along x (both rows packed); w's registers are dead before u is fetched
 		const float dyA = g.y - (byf + (float)q), dyB = g.y - (byf + (float)(q + 4));
 		const float dx0 = g.x - bxf;
-		f32x2 S0 = bc2(0.f), Sx = bc2(0.f), Sxx = bc2(0.f);
+		f32x2 S0, Sx, Sxx;
 		{
 			const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(srow + stage_row(q));
+			{ // k = 0 initialises the sums (no additions of a zero accumulator)
+				const ulonglong2 a = wp[0];
+				const f32x2 dxa = bc2(dx0), dxb = bc2(dx0 - 1.0f);
+				const f32x2 ta = mul2(a.x, dxa), tb = mul2(a.y, dxb);
+				S0 = add2(a.x, a.y);
+				Sx = add2(ta, tb);
+				Sxx = fma2(tb, dxb, mul2(ta, dxa));
+			}
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
+			for (int k = 1; k < 4; k++) {
 				const ulonglong2 a = wp[k];
 				const f32x2 dxa = bc2(dx0 - (float)(2 * k)), dxb = bc2(dx0 - (float)(2 * k + 1));
 				const f32x2 ta = mul2(a.x, dxa), tb = mul2(a.y, dxb);
